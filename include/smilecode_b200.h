@@ -1,0 +1,101 @@
+/* smilecode_b200 -- C ABI of the B200-native (sm_100a) ModeT registration hot path.
+ *
+ * Drop-in boundary.  The reference's only native interface is the pybind pair
+ *     modet_fw(query, key, rpb) -> attn          (ModeT-cu/modet/modet.cpp:4-18, include/utils.h:23-27)
+ *     modet_bw(d_attn, query, key, biasEnabled)  (ModeT-cu/modet/modet.cpp:20-31, include/utils.h:39-44)
+ * called from ModeT-cu/functional.py:5-28; every other step of the path is a torch library call
+ * inside ModeT/models.py.  This header is what a binding for the whole path binds instead: one
+ * entry point per reference function on the path, plain pointers and
+ * sizes, no torch types.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer to contiguous fp32 (fp64 where stated), 16-byte aligned;
+ *   - outputs are caller-allocated (the caller's allocator owns memory; the reference's callee-
+ *     allocated torch::zeros at modet_kernel.cu:115 is replaced by this);
+ *   - work is enqueued on `stream` (a cudaStream_t) and never synchronises the host
+ *     (reference: c10::cuda::getCurrentCUDAStream(), modet_kernel.cu:119,362);
+ *   - returns SMILE_OK (0) or a negative error code; smile_last_error() gives the message of the
+ *     last failure on the calling thread (reference: TORCH_CHECK -> RuntimeError, utils.h:7-14);
+ *   - no global mutable state besides the per-process TMA descriptor cache; re-entrant.
+ *   - volumes are [B, C, D, H, W] channels-first unless stated; "channels-last" is [B, D, H, W, C].
+ */
+#ifndef SMILECODE_B200_H
+#define SMILECODE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMILE_OK 0
+#define SMILE_ERR_INVALID_ARG (-1)
+#define SMILE_ERR_CUDA (-2)
+#define SMILE_ERR_UNSUPPORTED (-3)
+
+typedef void* smile_stream_t; /* cudaStream_t */
+
+/* Library version (major*10000 + minor*100 + patch) and last error text (thread-local). */
+int smile_version(void);
+const char* smile_last_error(void);
+
+/* a2  ModeTransformer.forward (ModeT/models.py:308-334; supersedes modet_fw + softmax + attn@v,
+ * ModeT-cu/models.py:304-314).  q, k: channels-last [B,D,H,W,heads*head_dim]; rpb: [heads,3,3,3]
+ * or NULL; out: [B,3*heads,D,H,W].  The key volume is zero padded and the padded taps stay in
+ * the softmax. */
+int smile_modet_attn_fwd(const float* q, const float* k, const float* rpb, float* out, int B, int D, int H, int W,
+                         int heads, int head_dim, float scale, smile_stream_t stream);
+
+/* a5  SpatialTransformer.forward (ModeT/models.py:49-67): out[b,c] = trilinear sample of src[b,c]
+ * at voxel + flow[b,:,voxel]; zeros padding, align_corners=True, integer corner indices bit-exact
+ * with torch.  src/out: [B,C,D,H,W]; flow: [B,3,D,H,W]. */
+int smile_warp3d_fwd(const float* src, const float* flow, float* out, int B, int C, int D, int H, int W,
+                     smile_stream_t stream);
+
+/* a6  nn.Upsample(scale_factor=2, 'trilinear', align_corners=True) (ModeT/models.py:354, 257-261)
+ * with the power-of-two pre-scale folded in: out = premul * up2(x).  x: [B,C,D,H,W] -> [B,C,2D,2H,2W]. */
+int smile_upsample2x_fwd(const float* x, float* out, int B, int C, int D, int H, int W, float premul,
+                         smile_stream_t stream);
+
+/* a6  flow composition (ModeT/models.py:392, 398, 403, 408):
+ * out = postmul * (SpatialTransformer(flow, w) + w); all [B,3,D,H,W]. */
+int smile_flow_compose_fwd(const float* flow, const float* w, float* out, int B, int D, int H, int W, float postmul,
+                           smile_stream_t stream);
+
+/* a2+a6+a5 fused, for the heads==1 pyramid levels (ModeT/models.py:401-403 and 406-410):
+ *   w        = ModeTransformer(q, k)                      (heads = 1)
+ *   flow_out = postmul * (SpatialTransformer(flow_in, w) + w)
+ *   moved    = SpatialTransformer(moving, flow_out)       (skipped when moved == NULL)
+ * q, k: channels-last [B,D,H,W,head_dim]; flow_in/flow_out: [B,3,D,H,W]; moving/moved: [B,Cmov,D,H,W]. */
+int smile_modet_fused_fwd(const float* q, const float* k, const float* rpb, const float* flow_in, const float* moving,
+                          float* flow_out, float* moved, int B, int D, int H, int W, int head_dim, float scale,
+                          float postmul, int Cmov, smile_stream_t stream);
+
+/* a7  ProjectionLayer.forward (ModeT/models.py:238-241): channels-first feat [B,Cin,N] ->
+ * LayerNorm(Linear(feat)) channels-last [B,N,C].  weight: [C,Cin]; bias, gamma, beta: [C]. */
+int smile_proj_ln_fwd(const float* feat, const float* weight, const float* bias, const float* gamma, const float* beta,
+                      float* out, int B, int Cin, int C, long long N, float eps, smile_stream_t stream);
+
+/* a8/a4 Conv3d(kernel 3, stride 1, padding 1) (ModeT/models.py:127, 143, 253).
+ *   in_stats  (fp64 [B*Cin][2] = sum, sum of squares of `in`) non-NULL: `in` is a raw conv output and
+ *             InstanceNorm3d(eps)+LeakyReLU(0.1) of it is applied on load (models.py:148-150);
+ *   out_stats (fp64 [B*Cout][2], zeroed by the caller) non-NULL: sum / sum of squares of the raw
+ *             output are accumulated into it for the following InstanceNorm;
+ *   act_out != 0: LeakyReLU(0.1) on the stored output (ConvBlock, models.py:131-132).
+ * weight: [Cout,Cin,3,3,3]; bias: [Cout]. */
+int smile_conv3d_fwd(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
+                     double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
+                     smile_stream_t stream);
+
+/* a8  InstanceNorm3d + LeakyReLU(0.1) from fp64 sums (models.py:149-150), and AvgPool3d(2)
+ * (models.py:198) of the result into `pooled` [B,C,D/2,H/2,W/2] when pooled != NULL.  out may alias raw. */
+int smile_instnorm_lrelu_pool_fwd(const float* raw, const double* stats, float* out, float* pooled, int B, int C, int D,
+                                  int H, int W, float eps, smile_stream_t stream);
+
+/* a4  CWM tail (ModeT/models.py:254, 268-275): out = 2 * sum_f fields[:,3f:3f+3] * softmax_f(logits).
+ * fields: [B,3F,N]; logits: [B,F,N]; out: [B,3,N]. */
+int smile_cwm_fuse_fwd(const float* fields, const float* logits, float* out, int B, int F, long long N,
+                       smile_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMILECODE_B200_H */

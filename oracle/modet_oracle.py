@@ -218,10 +218,29 @@ def encoder(x: Tensor, sd: Dict[str, Tensor], prefix: str = "encoder") -> List[T
 # --------------------------------------------------------------------------------------
 # a9  ModeT.forward   (ModeT/models.py:377-412)
 # --------------------------------------------------------------------------------------
+def _lib_warp(src: Tensor, flow: Tensor) -> Tensor:
+    """SpatialTransformer exactly as the reference spells it (models.py:51-67): torch's own
+    grid_sample does the sampling.  Used for the CPU-baseline timing leg."""
+    shape = flow.shape[2:]
+    idx = torch.stack(torch.meshgrid(*[torch.arange(0, s, dtype=flow.dtype) for s in shape], indexing="ij")).unsqueeze(0)
+    loc = idx + flow
+    for i, s in enumerate(shape):
+        loc[:, i] = 2 * (loc[:, i] / (s - 1) - 0.5)
+    return F.grid_sample(src, loc.permute(0, 2, 3, 4, 1)[..., [2, 1, 0]], align_corners=True, mode="bilinear")
+
+
+def _lib_up2(x: Tensor) -> Tensor:
+    return F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=True)   # models.py:354
+
+
 def modet_forward(moving: Tensor, fixed: Tensor, sd: Dict[str, Tensor], num_heads: Sequence[int] = (8, 4, 2, 1, 1),
-                  scale: float | None = 1.0, head_dim: int = 6) -> Tuple[Tensor, Tensor]:
-    """Coarse-to-fine pyramid.  `scale=None` means head_dim**-0.5 (models.py:285)."""
+                  scale: float | None = 1.0, head_dim: int = 6, library_ops: bool = False) -> Tuple[Tensor, Tensor]:
+    """Coarse-to-fine pyramid.  `scale=None` means head_dim**-0.5 (models.py:285).
+    library_ops=True swaps the elementary warp / upsample restatements for the torch library calls
+    the reference itself makes (same results, see tests) -- the faster, reference-like CPU timing."""
     sc = scale if scale else head_dim ** -0.5
+    warp_trilinear = _lib_warp if library_ops else globals()["warp_trilinear"]
+    upsample2x_trilinear = _lib_up2 if library_ops else globals()["upsample2x_trilinear"]
     M = encoder(moving, sd)
     Fx = encoder(fixed, sd)
 
@@ -232,7 +251,7 @@ def modet_forward(moving: Tensor, fixed: Tensor, sd: Dict[str, Tensor], num_head
         return modet_attention(q, k, sd[f"mdt{level}.rpb"], heads, sc)
 
     flow = cwm(attn(5, M[4]), sd, "cwm5")                                   # 383-386
-    w = cwm(attn(4, warp_trilinear(M[3], flow)), sd, "cwm4")               # 388-391
+    w = cwm(attn(4, warp_trilinear(M[3], flow)), sd, "cwm4")               # 388-391  (cwm keeps the restated upsample)
     up = upsample2x_trilinear(2 * flow)
     flow = warp_trilinear(up, w) + w                                        # 392
     w = cwm(attn(3, warp_trilinear(M[2], flow)), sd, "cwm3")               # 394-397

@@ -1,0 +1,60 @@
+"""ctypes binding of libsmilecode_b200.so (the C ABI declared in include/smilecode_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing or a call fails, the
+caller gets an exception.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_void_p
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsmilecode_b200.so")
+
+P = c_void_p
+# name -> argtypes, mirroring include/smilecode_b200.h one to one (tests/test_abi.py checks this)
+SIGNATURES = {
+    "smile_modet_attn_fwd": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P],
+    "smile_warp3d_fwd": [P, P, P, c_int, c_int, c_int, c_int, c_int, P],
+    "smile_upsample2x_fwd": [P, P, c_int, c_int, c_int, c_int, c_int, c_float, P],
+    "smile_flow_compose_fwd": [P, P, P, c_int, c_int, c_int, c_int, c_float, P],
+    "smile_modet_fused_fwd": [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, P],
+    "smile_proj_ln_fwd": [P, P, P, P, P, P, c_int, c_int, c_int, c_longlong, c_float, P],
+    "smile_conv3d_fwd": [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P],
+    "smile_instnorm_lrelu_pool_fwd": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P],
+    "smile_cwm_fuse_fwd": [P, P, P, c_int, c_int, c_longlong, P],
+}
+
+_lib = None
+
+
+class SmileError(RuntimeError):
+    """Raised when a C-ABI entry point returns a non-zero status."""
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SmileError(
+                f"{LIB_PATH} is missing: build it with `python -m smilecode_b200.build` "
+                "(nvcc, sm_100a).  smilecode_b200 has no CPU / PyTorch fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        handle.smile_version.restype = c_int
+        handle.smile_version.argtypes = []
+        handle.smile_last_error.restype = c_char_p
+        handle.smile_last_error.argtypes = []
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = c_int
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def call(name: str, *args) -> None:
+    handle = lib()
+    rc = getattr(handle, name)(*args)
+    if rc != 0:
+        msg = handle.smile_last_error()
+        raise SmileError(f"{name} failed (code {rc}): {msg.decode() if msg else '?'}")

@@ -1,0 +1,161 @@
+// Exported C ABI (include/smilecode_b200.h): argument validation + dispatch to the launchers.
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/smilecode_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace smile {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));
+    return SMILE_ERR_CUDA;
+  }
+  return SMILE_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace smile
+
+using namespace smile;
+
+#define REQUIRE(cond, ...)          \
+  do {                              \
+    if (!(cond)) {                  \
+      set_error(__VA_ARGS__);       \
+      return SMILE_ERR_INVALID_ARG; \
+    }                               \
+  } while (0)
+
+#define REQUIRE_PTR(p) REQUIRE((p) != nullptr && aligned16(p), "%s: pointer `" #p "` is NULL or not 16-byte aligned", __func__)
+#define REQUIRE_VOL(B, D, H, W)                                                                              \
+  REQUIRE((B) > 0 && (D) > 0 && (H) > 0 && (W) > 0 && (long long)(D) * (H) * (W) < (1LL << 31),              \
+          "%s: bad volume B=%d D=%d H=%d W=%d (each > 0, D*H*W < 2^31)", __func__, (B), (D), (H), (W))
+
+extern "C" {
+
+int smile_version(void) { return 100; }
+const char* smile_last_error(void) { return g_err; }
+
+int smile_modet_attn_fwd(const float* q, const float* k, const float* rpb, float* out, int B, int D, int H, int W,
+                         int heads, int head_dim, float scale, smile_stream_t stream) {
+  REQUIRE_PTR(q);
+  REQUIRE_PTR(k);
+  REQUIRE_PTR(out);
+  REQUIRE(rpb == nullptr || aligned16(rpb), "%s: rpb not 16-byte aligned", __func__);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(heads > 0 && head_dim > 0 && heads <= 256, "%s: heads=%d head_dim=%d out of range", __func__, heads, head_dim);
+  return launch_modet_attn(q, k, rpb, out, B, D, H, W, heads, head_dim, scale, (cudaStream_t)stream);
+}
+
+int smile_warp3d_fwd(const float* src, const float* flow, float* out, int B, int C, int D, int H, int W,
+                     smile_stream_t stream) {
+  REQUIRE_PTR(src);
+  REQUIRE_PTR(flow);
+  REQUIRE_PTR(out);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(C > 0, "%s: C=%d", __func__, C);
+  REQUIRE(src != out, "%s: out must not alias src", __func__);
+  return launch_warp3d(src, flow, out, B, C, D, H, W, (cudaStream_t)stream);
+}
+
+int smile_upsample2x_fwd(const float* x, float* out, int B, int C, int D, int H, int W, float premul,
+                         smile_stream_t stream) {
+  REQUIRE_PTR(x);
+  REQUIRE_PTR(out);
+  REQUIRE_VOL(B, 2 * D, 2 * H, 2 * W);
+  REQUIRE(C > 0, "%s: C=%d", __func__, C);
+  return launch_upsample2x(x, out, B, C, D, H, W, premul, (cudaStream_t)stream);
+}
+
+int smile_flow_compose_fwd(const float* flow, const float* w, float* out, int B, int D, int H, int W, float postmul,
+                           smile_stream_t stream) {
+  REQUIRE_PTR(flow);
+  REQUIRE_PTR(w);
+  REQUIRE_PTR(out);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(out != flow, "%s: out must not alias flow", __func__);
+  return launch_compose(flow, w, out, B, D, H, W, postmul, (cudaStream_t)stream);
+}
+
+int smile_modet_fused_fwd(const float* q, const float* k, const float* rpb, const float* flow_in, const float* moving,
+                          float* flow_out, float* moved, int B, int D, int H, int W, int head_dim, float scale,
+                          float postmul, int Cmov, smile_stream_t stream) {
+  REQUIRE_PTR(q);
+  REQUIRE_PTR(k);
+  REQUIRE_PTR(flow_in);
+  REQUIRE_PTR(flow_out);
+  REQUIRE(rpb == nullptr || aligned16(rpb), "%s: rpb not 16-byte aligned", __func__);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(head_dim > 0, "%s: head_dim=%d", __func__, head_dim);
+  REQUIRE(flow_out != flow_in, "%s: flow_out must not alias flow_in", __func__);
+  if (moved != nullptr) {
+    REQUIRE_PTR(moving);
+    REQUIRE(aligned16(moved) && Cmov > 0, "%s: moved misaligned or Cmov=%d", __func__, Cmov);
+  }
+  return launch_modet_fused(q, k, rpb, flow_in, moving, flow_out, moved, B, D, H, W, head_dim, scale, postmul, Cmov,
+                            (cudaStream_t)stream);
+}
+
+int smile_proj_ln_fwd(const float* feat, const float* weight, const float* bias, const float* gamma, const float* beta,
+                      float* out, int B, int Cin, int C, long long N, float eps, smile_stream_t stream) {
+  REQUIRE_PTR(feat);
+  REQUIRE_PTR(weight);
+  REQUIRE_PTR(bias);
+  REQUIRE_PTR(gamma);
+  REQUIRE_PTR(beta);
+  REQUIRE_PTR(out);
+  REQUIRE(B > 0 && Cin > 0 && C > 0 && N > 0 && N < (1LL << 31), "%s: bad sizes B=%d Cin=%d C=%d N=%lld", __func__, B, Cin,
+          C, N);
+  return launch_proj_ln(feat, weight, bias, gamma, beta, out, B, Cin, C, N, eps, (cudaStream_t)stream);
+}
+
+int smile_conv3d_fwd(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
+                     double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
+                     smile_stream_t stream) {
+  REQUIRE_PTR(in);
+  REQUIRE_PTR(weight);
+  REQUIRE_PTR(bias);
+  REQUIRE_PTR(out);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(Cin > 0 && Cout > 0 && Cin <= 4096 && Cout <= 4096, "%s: Cin=%d Cout=%d out of range", __func__, Cin, Cout);
+  REQUIRE(in != out, "%s: out must not alias in", __func__);
+  REQUIRE((long long)B <= 65535, "%s: B=%d exceeds grid.z", __func__, B);
+  return launch_conv3d(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps,
+                       (cudaStream_t)stream);
+}
+
+int smile_instnorm_lrelu_pool_fwd(const float* raw, const double* stats, float* out, float* pooled, int B, int C, int D,
+                                  int H, int W, float eps, smile_stream_t stream) {
+  REQUIRE_PTR(raw);
+  REQUIRE_PTR(stats);
+  REQUIRE_PTR(out);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(C > 0 && (long long)B * C <= 65535, "%s: B*C=%lld out of range", __func__, (long long)B * C);
+  REQUIRE(pooled == nullptr || (D >= 2 && H >= 2 && W >= 2), "%s: pooling needs every dim >= 2", __func__);
+  return launch_in_finalize(raw, stats, out, pooled, B, C, D, H, W, eps, (cudaStream_t)stream);
+}
+
+int smile_cwm_fuse_fwd(const float* fields, const float* logits, float* out, int B, int F, long long N,
+                       smile_stream_t stream) {
+  REQUIRE_PTR(fields);
+  REQUIRE_PTR(logits);
+  REQUIRE_PTR(out);
+  REQUIRE(B > 0 && F > 0 && N > 0 && N < (1LL << 31), "%s: bad sizes B=%d F=%d N=%lld", __func__, B, F, N);
+  return launch_cwm_fuse(fields, logits, out, B, F, N, (cudaStream_t)stream);
+}
+
+}  // extern "C"

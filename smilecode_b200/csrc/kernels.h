@@ -1,0 +1,32 @@
+// Internal launch entry points (C++ linkage); the exported C ABI lives in capi.cu / include/smilecode_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace smile {
+
+// warp.cu
+int launch_warp3d(const float* src, const float* flow, float* out, int B, int C, int D, int H, int W, cudaStream_t st);
+int launch_compose(const float* flow, const float* w, float* out, int B, int D, int H, int W, float post, cudaStream_t st);
+int launch_upsample2x(const float* x, float* out, int B, int C, int D, int H, int W, float pre, cudaStream_t st);
+
+// attn.cu
+int launch_modet_attn(const float* q, const float* k, const float* rpb, float* out, int B, int D, int H, int W,
+                      int heads, int hd, float scale, cudaStream_t st);
+// fused heads==1 level: w = attn(q,k); flow_out = post*(T(flow_in, w) + w); optionally moved = T(moving, flow_out)
+int launch_modet_fused(const float* q, const float* k, const float* rpb, const float* flow_in, const float* moving,
+                       float* flow_out, float* moved, int B, int D, int H, int W, int hd, float scale, float post,
+                       int Cmov, cudaStream_t st);
+
+// proj.cu
+int launch_proj_ln(const float* feat, const float* weight, const float* bias, const float* gamma, const float* beta,
+                   float* out, int B, int Cin, int C, long long N, float eps, cudaStream_t st);
+
+// conv.cu
+int launch_conv3d(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
+                  double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
+                  cudaStream_t st);
+int launch_in_finalize(const float* raw, const double* stats, float* out, float* pooled, int B, int C, int D, int H,
+                       int W, float eps, cudaStream_t st);
+int launch_cwm_fuse(const float* fields, const float* logits, float* out, int B, int F, long long N, cudaStream_t st);
+
+}  // namespace smile

@@ -1,0 +1,190 @@
+"""Tensor-level operators of the ModeT hot path: thin wrappers that validate torch tensors,
+allocate outputs through torch's caching allocator and enqueue the sm_100a kernels on torch's
+current stream through the C ABI (`_lib.call`).  PyTorch is plumbing here (memory + streams);
+every arithmetic step runs in libsmilecode_b200.so.  No fallbacks.
+
+Reference functions replaced are cited per operator (paths under the reference tree).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from ._lib import SmileError, call
+
+Tensor = torch.Tensor
+IN_EPS = 1e-5  # nn.InstanceNorm3d / nn.LayerNorm default eps (ModeT/models.py:144, 233)
+
+
+def _chk(t: Tensor, name: str, ndim: int, dtype=torch.float32) -> Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise SmileError(f"{name} must be a CUDA tensor (smilecode_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise SmileError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.dim() != ndim:
+        raise SmileError(f"{name} must have {ndim} dims, got shape {tuple(t.shape)}")
+    if t.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError(
+            f"{name} requires grad: the backward kernels of smilecode_b200 are not built yet; "
+            "wrap the call in torch.no_grad()")
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16 != 0:
+        t = t.clone()
+    return t
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def modet_attention(q: Tensor, k: Tensor, rpb: Optional[Tensor], heads: int, scale: float) -> Tensor:
+    """ModeTransformer.forward (ModeT/models.py:308-334).  q,k [B,D,H,W,C] -> [B,3*heads,D,H,W]."""
+    q = _chk(q, "q", 5)
+    k = _chk(k, "k", 5)
+    if q.shape != k.shape:
+        raise SmileError(f"q {tuple(q.shape)} and k {tuple(k.shape)} differ")
+    B, D, H, W, C = q.shape
+    if C % heads:
+        raise SmileError(f"channels {C} not divisible by heads {heads}")
+    if rpb is not None:
+        rpb = _chk(rpb, "rpb", 4)
+        if tuple(rpb.shape) != (heads, 3, 3, 3):
+            raise SmileError(f"rpb must be [{heads},3,3,3], got {tuple(rpb.shape)}")
+    out = torch.empty((B, 3 * heads, D, H, W), device=q.device, dtype=torch.float32)
+    call("smile_modet_attn_fwd", q.data_ptr(), k.data_ptr(), _ptr(rpb), out.data_ptr(), B, D, H, W, heads, C // heads,
+         float(scale), _stream())
+    return out
+
+
+def warp3d(src: Tensor, flow: Tensor) -> Tensor:
+    """SpatialTransformer.forward, bilinear mode (ModeT/models.py:49-67)."""
+    src = _chk(src, "src", 5)
+    flow = _chk(flow, "flow", 5)
+    B, C, D, H, W = src.shape
+    if tuple(flow.shape) != (B, 3, D, H, W):
+        raise SmileError(f"flow must be [{B},3,{D},{H},{W}], got {tuple(flow.shape)}")
+    out = torch.empty_like(src)
+    call("smile_warp3d_fwd", src.data_ptr(), flow.data_ptr(), out.data_ptr(), B, C, D, H, W, _stream())
+    return out
+
+
+def upsample2x(x: Tensor, premul: float = 1.0) -> Tensor:
+    """premul * nn.Upsample(scale_factor=2, trilinear, align_corners=True)(x) (ModeT/models.py:354)."""
+    x = _chk(x, "x", 5)
+    B, C, D, H, W = x.shape
+    out = torch.empty((B, C, 2 * D, 2 * H, 2 * W), device=x.device, dtype=torch.float32)
+    call("smile_upsample2x_fwd", x.data_ptr(), out.data_ptr(), B, C, D, H, W, float(premul), _stream())
+    return out
+
+
+def flow_compose(flow: Tensor, w: Tensor, postmul: float = 1.0) -> Tensor:
+    """postmul * (SpatialTransformer(flow, w) + w) (ModeT/models.py:392, 398, 403, 408)."""
+    flow = _chk(flow, "flow", 5)
+    w = _chk(w, "w", 5)
+    B, three, D, H, W = flow.shape
+    if three != 3 or w.shape != flow.shape:
+        raise SmileError(f"flow {tuple(flow.shape)} / w {tuple(w.shape)} must both be [B,3,D,H,W]")
+    out = torch.empty_like(flow)
+    call("smile_flow_compose_fwd", flow.data_ptr(), w.data_ptr(), out.data_ptr(), B, D, H, W, float(postmul), _stream())
+    return out
+
+
+def modet_fused(q: Tensor, k: Tensor, rpb: Optional[Tensor], flow_in: Tensor, moving: Optional[Tensor], scale: float,
+                postmul: float = 1.0) -> Tuple[Tensor, Optional[Tensor]]:
+    """heads==1 level in one kernel (ModeT/models.py:401-403, 406-410):
+    w = mdt(q,k); flow_out = postmul*(T(flow_in,w)+w); moved = T(moving, flow_out) if moving is given."""
+    q = _chk(q, "q", 5)
+    k = _chk(k, "k", 5)
+    flow_in = _chk(flow_in, "flow_in", 5)
+    B, D, H, W, hd = q.shape
+    if k.shape != q.shape or tuple(flow_in.shape) != (B, 3, D, H, W):
+        raise SmileError("modet_fused: q/k/flow_in shapes disagree")
+    if rpb is not None:
+        rpb = _chk(rpb, "rpb", 4)
+        if tuple(rpb.shape) != (1, 3, 3, 3):
+            raise SmileError("modet_fused handles heads == 1 only (rpb must be [1,3,3,3])")
+    flow_out = torch.empty_like(flow_in)
+    moved = None
+    cm = 0
+    if moving is not None:
+        moving = _chk(moving, "moving", 5)
+        cm = moving.shape[1]
+        if tuple(moving.shape) != (B, cm, D, H, W):
+            raise SmileError("modet_fused: moving must be [B,C,D,H,W] at the flow resolution")
+        moved = torch.empty_like(moving)
+    call("smile_modet_fused_fwd", q.data_ptr(), k.data_ptr(), _ptr(rpb), flow_in.data_ptr(), _ptr(moving),
+         flow_out.data_ptr(), _ptr(moved), B, D, H, W, hd, float(scale), float(postmul), cm, _stream())
+    return flow_out, moved
+
+
+def proj_ln(feat: Tensor, weight: Tensor, bias: Tensor, gamma: Tensor, beta: Tensor, eps: float = IN_EPS) -> Tensor:
+    """ProjectionLayer.forward (ModeT/models.py:238-241): [B,Cin,D,H,W] -> [B,D,H,W,C]."""
+    feat = _chk(feat, "feat", 5)
+    weight = _chk(weight, "proj.weight", 2)
+    B, Cin, D, H, W = feat.shape
+    C = weight.shape[0]
+    if weight.shape[1] != Cin:
+        raise SmileError(f"proj.weight {tuple(weight.shape)} does not match Cin={Cin}")
+    bias, gamma, beta = _chk(bias, "proj.bias", 1), _chk(gamma, "norm.weight", 1), _chk(beta, "norm.bias", 1)
+    out = torch.empty((B, D, H, W, C), device=feat.device, dtype=torch.float32)
+    call("smile_proj_ln_fwd", feat.data_ptr(), weight.data_ptr(), bias.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+         out.data_ptr(), B, Cin, C, D * H * W, float(eps), _stream())
+    return out
+
+
+def conv3d(x: Tensor, weight: Tensor, bias: Tensor, in_stats: Optional[Tensor] = None, want_stats: bool = False,
+           act_out: bool = False, eps: float = IN_EPS) -> Tuple[Tensor, Optional[Tensor]]:
+    """Conv3d(k=3, s=1, p=1) (ModeT/models.py:127, 143, 253).  With `in_stats` the input is a raw conv
+    output whose InstanceNorm+LeakyReLU is applied on load; with `want_stats` the fp64 (sum, sumsq)
+    of the raw output per (b, c) are returned for the next InstanceNorm."""
+    x = _chk(x, "x", 5)
+    weight = _chk(weight, "weight", 5)
+    bias = _chk(bias, "bias", 1)
+    B, Cin, D, H, W = x.shape
+    Cout = weight.shape[0]
+    if tuple(weight.shape) != (Cout, Cin, 3, 3, 3):
+        raise SmileError(f"weight must be [{Cout},{Cin},3,3,3], got {tuple(weight.shape)}")
+    if in_stats is not None:
+        in_stats = _chk(in_stats, "in_stats", 2, torch.float64)
+        if tuple(in_stats.shape) != (B * Cin, 2):
+            raise SmileError("in_stats must be [B*Cin, 2] float64")
+    out = torch.empty((B, Cout, D, H, W), device=x.device, dtype=torch.float32)
+    stats = torch.zeros((B * Cout, 2), device=x.device, dtype=torch.float64) if want_stats else None
+    call("smile_conv3d_fwd", x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), _ptr(in_stats), _ptr(stats),
+         B, Cin, Cout, D, H, W, int(act_out), float(eps), _stream())
+    return out, stats
+
+
+def instnorm_lrelu_pool(raw: Tensor, stats: Tensor, pool: bool = False, inplace: bool = False,
+                        eps: float = IN_EPS) -> Tuple[Tensor, Optional[Tensor]]:
+    """InstanceNorm3d + LeakyReLU(0.1) (ModeT/models.py:149-150) from fp64 sums; optionally also
+    AvgPool3d(2) of the result (models.py:198)."""
+    raw = _chk(raw, "raw", 5)
+    stats = _chk(stats, "stats", 2, torch.float64)
+    B, C, D, H, W = raw.shape
+    out = raw if inplace else torch.empty_like(raw)
+    pooled = torch.empty((B, C, D // 2, H // 2, W // 2), device=raw.device, dtype=torch.float32) if pool else None
+    call("smile_instnorm_lrelu_pool_fwd", raw.data_ptr(), stats.data_ptr(), out.data_ptr(), _ptr(pooled), B, C, D, H, W,
+         float(eps), _stream())
+    return out, pooled
+
+
+def cwm_fuse(fields: Tensor, logits: Tensor) -> Tensor:
+    """CWM tail (ModeT/models.py:254, 268-275): 2 * sum_f fields[:, 3f:3f+3] * softmax(logits)[:, f]."""
+    fields = _chk(fields, "fields", 5)
+    logits = _chk(logits, "logits", 5)
+    B, F3, D, H, W = fields.shape
+    F = logits.shape[1]
+    if F3 != 3 * F or tuple(logits.shape) != (B, F, D, H, W):
+        raise SmileError(f"fields {tuple(fields.shape)} / logits {tuple(logits.shape)} mismatch")
+    out = torch.empty((B, 3, D, H, W), device=fields.device, dtype=torch.float32)
+    call("smile_cwm_fuse_fwd", fields.data_ptr(), logits.data_ptr(), out.data_ptr(), B, F, D * H * W, _stream())
+    return out

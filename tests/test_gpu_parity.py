@@ -1,0 +1,224 @@
+"""CUDA path (through the C ABI) vs the CPU oracle and the reference-generated golden vectors.
+Tolerances: bit exact for the warp (integer corner indices + non-contracted arithmetic);
+<= 1e-4 relative fp32 elsewhere as BASELINE.json's north_star states (actual errors ~1e-6)."""
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from oracle import modet_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(t):
+    return t.cuda().contiguous()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from smilecode_b200 import ops as _ops
+    return _ops
+
+
+def rel_err(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+# ------------------------------------------------------------------ a2 attention
+@pytest.mark.parametrize("name", golden_names("attn_"))
+def test_attention_golden(ops, name):
+    g = load_golden(name)
+    with torch.no_grad():
+        out = ops.modet_attention(dev(g["q"]), dev(g["k"]), dev(g["rpb"]), int(g["heads"]), float(g["scale"])).cpu()
+    assert out.shape == g["out"].shape
+    assert (out - g["out"]).abs().max() <= 2e-6
+
+
+@pytest.mark.parametrize("shape,heads,hd", [((1, 9, 11, 13), 1, 6), ((2, 4, 6, 34), 2, 6), ((1, 8, 16, 64), 1, 6),
+                                            ((1, 12, 24, 40), 1, 6), ((1, 3, 5, 7), 3, 5), ((1, 6, 6, 6), 8, 6),
+                                            ((2, 7, 9, 10), 4, 8), ((1, 5, 4, 6), 2, 4)])
+def test_attention_oracle(ops, shape, heads, hd):
+    B, D, H, W = shape
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(B, D, H, W, heads * hd, generator=g)
+    k = torch.randn(B, D, H, W, heads * hd, generator=g)
+    rpb = torch.randn(heads, 3, 3, 3, generator=g) * 0.5
+    for scale, r in ((1.0, rpb), (hd ** -0.5, None)):
+        ref = orc.modet_attention(q, k, r, heads, scale)
+        out = ops.modet_attention(dev(q), dev(k), None if r is None else dev(r), heads, scale).cpu()
+        assert (out - ref).abs().max() <= 3e-6
+
+
+# ------------------------------------------------------------------ a5 warp
+@pytest.mark.parametrize("name", golden_names("warp_"))
+def test_warp_golden_bit_exact(ops, name):
+    g = load_golden(name)
+    out = ops.warp3d(dev(g["src"]), dev(g["flow"])).cpu()
+    assert torch.equal(out, g["out"])
+
+
+@pytest.mark.parametrize("shape", [(160, 6, 192), (10, 12, 10), (20, 24, 20), (40, 48, 40), (2, 2, 2), (7, 80, 96)])
+def test_warp_identity_indices(ops, shape):
+    """Zero flow: the fp32 normalise/un-normalise round trip moves floor() at many integer
+    coordinates; the kernel must reproduce torch bit for bit, not return src."""
+    g = torch.Generator().manual_seed(3)
+    src = torch.randn(1, 2, *shape, generator=g)
+    flow = torch.zeros(1, 3, *shape)
+    ref = orc.warp_trilinear(src, flow)
+    out = ops.warp3d(dev(src), dev(flow)).cpu()
+    assert torch.equal(out, ref)
+    # integer flows land exactly on (shifted) voxels in exact arithmetic; same check
+    flow = torch.randint(-3, 4, (1, 3, *shape), generator=g).float()
+    assert torch.equal(ops.warp3d(dev(src), dev(flow)).cpu(), orc.warp_trilinear(src, flow))
+
+
+def test_warp_random_bit_exact(ops):
+    g = torch.Generator().manual_seed(4)
+    src = torch.randn(2, 5, 12, 17, 33, generator=g)
+    flow = torch.randn(2, 3, 12, 17, 33, generator=g) * 4
+    assert torch.equal(ops.warp3d(dev(src), dev(flow)).cpu(), orc.warp_trilinear(src, flow))
+
+
+# ------------------------------------------------------------------ a6 upsample / compose
+@pytest.mark.parametrize("name", golden_names("up2_"))
+def test_upsample_golden(ops, name):
+    g = load_golden(name)
+    out = ops.upsample2x(dev(g["x"])).cpu()
+    assert (out - g["out"]).abs().max() <= 1e-6
+    out2 = ops.upsample2x(dev(g["x"]), 2.0).cpu()
+    assert torch.equal(out2, 2 * out)
+
+
+def test_compose_oracle(ops):
+    g = torch.Generator().manual_seed(6)
+    flow = torch.randn(2, 3, 10, 12, 14, generator=g) * 3
+    w = torch.rand(2, 3, 10, 12, 14, generator=g) * 2 - 1
+    for post in (1.0, 2.0):
+        ref = post * (orc.warp_trilinear(flow, w) + w)
+        assert torch.equal(ops.flow_compose(dev(flow), dev(w), post).cpu(), ref)
+
+
+# ------------------------------------------------------------------ a7 projection
+@pytest.mark.parametrize("name", golden_names("proj_"))
+def test_projection_golden(ops, name):
+    g = load_golden(name)
+    p = {k[2:]: v for k, v in g.items() if k.startswith("p.")}
+    out = ops.proj_ln(dev(g["x"]), dev(p["proj.weight"]), dev(p["proj.bias"]), dev(p["norm.weight"]),
+                      dev(p["norm.bias"])).cpu()
+    assert out.shape == g["out"].shape
+    assert (out - g["out"]).abs().max() <= 5e-6
+
+
+# ------------------------------------------------------------------ conv / IN / CWM / encoder
+@pytest.mark.parametrize("cin,cout,shape", [(1, 4, (6, 9, 40)), (4, 8, (5, 7, 33)), (8, 8, (8, 8, 32)),
+                                            (6, 12, (4, 10, 14)), (16, 16, (5, 6, 7)), (24, 3, (3, 4, 5)),
+                                            (128, 128, (2, 3, 2)), (12, 2, (9, 5, 26))])
+def test_conv3d_oracle(ops, cin, cout, shape):
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, cin, *shape, generator=g)
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    ref = orc.conv3(x, w, b)
+    out, st = ops.conv3d(dev(x), dev(w), dev(b), want_stats=True)
+    assert rel_err(out.cpu(), ref) <= 2e-6
+    st = st.cpu().reshape(2, cout, 2)
+    assert torch.allclose(st[..., 0], ref.double().sum(dim=(2, 3, 4)), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(st[..., 1], (ref.double() ** 2).sum(dim=(2, 3, 4)), rtol=1e-5, atol=1e-3)
+    # ConvInsBlock + ConvBlock semantics
+    y, _ = ops.instnorm_lrelu_pool(out, dev(st.reshape(-1, 2)), pool=False)
+    assert (y.cpu() - orc.lrelu(orc.instance_norm(ref))).abs().max() <= 2e-5
+    act, _ = ops.conv3d(dev(x), dev(w), dev(b), act_out=True)
+    assert rel_err(act.cpu(), orc.lrelu(ref)) <= 2e-6
+
+
+def test_conv_norm_on_load_and_pool(ops):
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(1, 4, 6, 8, 10, generator=g)
+    w1 = torch.randn(8, 4, 3, 3, 3, generator=g) * 0.1
+    w2 = torch.randn(8, 8, 3, 3, 3, generator=g) * 0.1
+    b1, b2 = torch.randn(8, generator=g) * 0.1, torch.randn(8, generator=g) * 0.1
+    t = orc.lrelu(orc.instance_norm(orc.conv3(x, w1, b1)))
+    ref = orc.lrelu(orc.instance_norm(orc.conv3(t, w2, b2)))
+    raw, st = ops.conv3d(dev(x), dev(w1), dev(b1), want_stats=True)
+    raw2, st2 = ops.conv3d(raw, dev(w2), dev(b2), in_stats=st, want_stats=True)
+    out, pooled = ops.instnorm_lrelu_pool(raw2, st2, pool=True)
+    assert (out.cpu() - ref).abs().max() <= 2e-5
+    assert (pooled.cpu() - torch.nn.functional.avg_pool3d(ref, 2)).abs().max() <= 2e-5
+
+
+@pytest.mark.parametrize("name", golden_names("cwm_"))
+def test_cwm_golden(name):
+    from smilecode_b200 import models
+    g = load_golden(name)
+    heads = g["x"].shape[1] // 3
+    m = models.CWM(3 * heads, 6 * heads)
+    m.load_state_dict({k[2:]: v for k, v in g.items() if k.startswith("p.")}, strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        out = m(dev(g["x"])).cpu()
+    assert (out - g["out"]).abs().max() <= 1e-5
+
+
+def test_encoder_golden():
+    from smilecode_b200 import models
+    g = load_golden("encoder_b2_16x16x32")
+    sd = orc.synth_state_dict(seed=1234)
+    enc = models.Encoder(1, 4)
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}, strict=True)
+    enc = enc.cuda().eval()
+    with torch.no_grad():
+        outs = enc(dev(g["x"]))
+    for i, o in enumerate(outs):
+        assert (o.cpu() - g[f"out{i}"]).abs().max() <= (3e-5 if i < 4 else 2e-4), i
+
+
+# ------------------------------------------------------------------ fused heads==1 level
+@pytest.mark.parametrize("shape", [(1, 6, 7, 9), (2, 8, 16, 32), (1, 12, 24, 64), (1, 5, 8, 66)])
+def test_fused_matches_unfused(ops, shape):
+    B, D, H, W = shape
+    g = torch.Generator().manual_seed(10)
+    q = torch.randn(B, D, H, W, 6, generator=g)
+    k = torch.randn(B, D, H, W, 6, generator=g)
+    rpb = torch.randn(1, 3, 3, 3, generator=g) * 0.5
+    flow = torch.randn(B, 3, D, H, W, generator=g) * 2
+    mov = torch.rand(B, 1, D, H, W, generator=g)
+    w = orc.modet_attention(q, k, rpb, 1, 1.0)
+    for post in (1.0, 2.0):
+        f_ref = post * (orc.warp_trilinear(flow, w) + w)
+        m_ref = orc.warp_trilinear(mov, f_ref)
+        f, m = ops.modet_fused(dev(q), dev(k), dev(rpb), dev(flow), dev(mov), 1.0, post)
+        assert (f.cpu() - f_ref).abs().max() <= 1e-5
+        assert (m.cpu() - m_ref).abs().max() <= 1e-5
+        f_only, none = ops.modet_fused(dev(q), dev(k), dev(rpb), dev(flow), None, 1.0, post)
+        assert none is None and torch.equal(f_only, f)
+
+
+# ------------------------------------------------------------------ a9 end to end
+@pytest.mark.parametrize("name", golden_names("e2e_"))
+def test_end_to_end_golden(name):
+    from smilecode_b200 import models
+    from smilecode_b200.synth import make_pair
+    g = load_golden(name)
+    heads = [int(h) for h in g["num_heads"]]
+    shape = tuple(g["flow"].shape[2:])
+    sd = orc.synth_state_dict(seed=1234, num_heads=heads)
+    model = models.ModeT(shape, head_dim=6, num_heads=heads, scale=1)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.endswith("grid") for k in missing)
+    model = model.cuda().eval()
+    moving, fixed = make_pair(shape, batch=1, seed=24)
+    with torch.no_grad():
+        moved, flow = model(dev(moving), dev(fixed))
+    err_ref = float((flow.cpu() - g["flow"]).abs().max())
+    err_64 = float((flow.cpu() - g["flow_fp64"]).abs().max())
+    floor = float((g["flow"] - g["flow_fp64"]).abs().max())
+    print(f"{name}: |ours-ref_fp32|={err_ref:.2e} |ours-ref_fp64|={err_64:.2e} |ref_fp32-ref_fp64|={floor:.2e}")
+    assert err_ref <= 1e-4
+    assert (moved.cpu() - g["moved"]).abs().max() <= 1e-4
+
+
+def test_errors_are_loud(ops):
+    with pytest.raises(Exception):
+        ops.warp3d(torch.zeros(1, 1, 4, 4, 4), torch.zeros(1, 3, 4, 4, 4))        # CPU tensors: no fallback
+    with pytest.raises(Exception):
+        ops.modet_attention(torch.zeros(1, 2, 2, 2, 6, device="cuda"), torch.zeros(1, 2, 2, 3, 6, device="cuda"), None, 1, 1.0)

@@ -84,3 +84,14 @@ def test_losses():
     g = load_golden("losses_12x14x11")
     assert abs(float(orc.ncc_vxm(g["a"], g["b"])) - g["ncc"]) <= 1e-6
     assert abs(float(orc.grad3d_l2(g["flow"])) - g["grad"]) <= 1e-7
+
+
+def test_library_ops_variant_matches():
+    """The timing variant of the oracle (torch grid_sample / interpolate, as the reference calls them)
+    must agree with the elementary restatement."""
+    heads = [8, 4, 2, 1, 1]
+    sd = orc.synth_state_dict(seed=1234, num_heads=heads)
+    moving, fixed = make_pair((32, 32, 32), batch=1, seed=24)
+    a = orc.modet_forward(moving, fixed, sd, num_heads=heads, scale=1.0)
+    b = orc.modet_forward(moving, fixed, sd, num_heads=heads, scale=1.0, library_ops=True)
+    assert (a[1] - b[1]).abs().max() <= 2e-5 and (a[0] - b[0]).abs().max() <= 2e-5

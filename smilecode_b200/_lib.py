@@ -52,9 +52,38 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
-def call(name: str, *args) -> None:
+LAUNCHES = 0          # number of C-ABI kernel launches issued by this process (bench.py reports it)
+_profile = None       # optional {label: [cuda event pairs]} filled when profiling is on
+
+
+def profile_start() -> None:
+    global _profile
+    _profile = {}
+
+
+def profile_stop():
+    """Returns {label: (calls, total_ms)} measured with CUDA events around every C-ABI call."""
+    global _profile
+    import torch
+    torch.cuda.synchronize()
+    out = {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (_profile or {}).items()}
+    _profile = None
+    return out
+
+
+def call(name: str, *args, label: str = "") -> None:
+    global LAUNCHES
     handle = lib()
-    rc = getattr(handle, name)(*args)
+    LAUNCHES += 1
+    if _profile is not None:
+        import torch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = getattr(handle, name)(*args)
+        b.record()
+        _profile.setdefault(f"{name}{label}", []).append((a, b))
+    else:
+        rc = getattr(handle, name)(*args)
     if rc != 0:
         msg = handle.smile_last_error()
         raise SmileError(f"{name} failed (code {rc}): {msg.decode() if msg else '?'}")

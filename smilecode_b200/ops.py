@@ -60,7 +60,7 @@ def modet_attention(q: Tensor, k: Tensor, rpb: Optional[Tensor], heads: int, sca
             raise SmileError(f"rpb must be [{heads},3,3,3], got {tuple(rpb.shape)}")
     out = torch.empty((B, 3 * heads, D, H, W), device=q.device, dtype=torch.float32)
     call("smile_modet_attn_fwd", q.data_ptr(), k.data_ptr(), _ptr(rpb), out.data_ptr(), B, D, H, W, heads, C // heads,
-         float(scale), _stream())
+         float(scale), _stream(), label=f"[h{heads} {D}x{H}x{W}]")
     return out
 
 
@@ -72,7 +72,8 @@ def warp3d(src: Tensor, flow: Tensor) -> Tensor:
     if tuple(flow.shape) != (B, 3, D, H, W):
         raise SmileError(f"flow must be [{B},3,{D},{H},{W}], got {tuple(flow.shape)}")
     out = torch.empty_like(src)
-    call("smile_warp3d_fwd", src.data_ptr(), flow.data_ptr(), out.data_ptr(), B, C, D, H, W, _stream())
+    call("smile_warp3d_fwd", src.data_ptr(), flow.data_ptr(), out.data_ptr(), B, C, D, H, W, _stream(),
+         label=f"[c{C} {D}x{H}x{W}]")
     return out
 
 
@@ -81,7 +82,8 @@ def upsample2x(x: Tensor, premul: float = 1.0) -> Tensor:
     x = _chk(x, "x", 5)
     B, C, D, H, W = x.shape
     out = torch.empty((B, C, 2 * D, 2 * H, 2 * W), device=x.device, dtype=torch.float32)
-    call("smile_upsample2x_fwd", x.data_ptr(), out.data_ptr(), B, C, D, H, W, float(premul), _stream())
+    call("smile_upsample2x_fwd", x.data_ptr(), out.data_ptr(), B, C, D, H, W, float(premul), _stream(),
+         label=f"[c{C} {D}x{H}x{W}]")
     return out
 
 
@@ -93,7 +95,8 @@ def flow_compose(flow: Tensor, w: Tensor, postmul: float = 1.0) -> Tensor:
     if three != 3 or w.shape != flow.shape:
         raise SmileError(f"flow {tuple(flow.shape)} / w {tuple(w.shape)} must both be [B,3,D,H,W]")
     out = torch.empty_like(flow)
-    call("smile_flow_compose_fwd", flow.data_ptr(), w.data_ptr(), out.data_ptr(), B, D, H, W, float(postmul), _stream())
+    call("smile_flow_compose_fwd", flow.data_ptr(), w.data_ptr(), out.data_ptr(), B, D, H, W, float(postmul), _stream(),
+         label=f"[{D}x{H}x{W}]")
     return out
 
 
@@ -121,7 +124,8 @@ def modet_fused(q: Tensor, k: Tensor, rpb: Optional[Tensor], flow_in: Tensor, mo
             raise SmileError("modet_fused: moving must be [B,C,D,H,W] at the flow resolution")
         moved = torch.empty_like(moving)
     call("smile_modet_fused_fwd", q.data_ptr(), k.data_ptr(), _ptr(rpb), flow_in.data_ptr(), _ptr(moving),
-         flow_out.data_ptr(), _ptr(moved), B, D, H, W, hd, float(scale), float(postmul), cm, _stream())
+         flow_out.data_ptr(), _ptr(moved), B, D, H, W, hd, float(scale), float(postmul), cm, _stream(),
+         label=f"[{D}x{H}x{W} mov{cm}]")
     return flow_out, moved
 
 
@@ -136,7 +140,7 @@ def proj_ln(feat: Tensor, weight: Tensor, bias: Tensor, gamma: Tensor, beta: Ten
     bias, gamma, beta = _chk(bias, "proj.bias", 1), _chk(gamma, "norm.weight", 1), _chk(beta, "norm.bias", 1)
     out = torch.empty((B, D, H, W, C), device=feat.device, dtype=torch.float32)
     call("smile_proj_ln_fwd", feat.data_ptr(), weight.data_ptr(), bias.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-         out.data_ptr(), B, Cin, C, D * H * W, float(eps), _stream())
+         out.data_ptr(), B, Cin, C, D * H * W, float(eps), _stream(), label=f"[{Cin}->{C} {D}x{H}x{W}]")
     return out
 
 
@@ -159,7 +163,7 @@ def conv3d(x: Tensor, weight: Tensor, bias: Tensor, in_stats: Optional[Tensor] =
     out = torch.empty((B, Cout, D, H, W), device=x.device, dtype=torch.float32)
     stats = torch.zeros((B * Cout, 2), device=x.device, dtype=torch.float64) if want_stats else None
     call("smile_conv3d_fwd", x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), _ptr(in_stats), _ptr(stats),
-         B, Cin, Cout, D, H, W, int(act_out), float(eps), _stream())
+         B, Cin, Cout, D, H, W, int(act_out), float(eps), _stream(), label=f"[{Cin}->{Cout} {D}x{H}x{W}]")
     return out, stats
 
 
@@ -173,7 +177,7 @@ def instnorm_lrelu_pool(raw: Tensor, stats: Tensor, pool: bool = False, inplace:
     out = raw if inplace else torch.empty_like(raw)
     pooled = torch.empty((B, C, D // 2, H // 2, W // 2), device=raw.device, dtype=torch.float32) if pool else None
     call("smile_instnorm_lrelu_pool_fwd", raw.data_ptr(), stats.data_ptr(), out.data_ptr(), _ptr(pooled), B, C, D, H, W,
-         float(eps), _stream())
+         float(eps), _stream(), label=f"[c{C} {D}x{H}x{W}]")
     return out, pooled
 
 
@@ -186,5 +190,6 @@ def cwm_fuse(fields: Tensor, logits: Tensor) -> Tensor:
     if F3 != 3 * F or tuple(logits.shape) != (B, F, D, H, W):
         raise SmileError(f"fields {tuple(fields.shape)} / logits {tuple(logits.shape)} mismatch")
     out = torch.empty((B, 3, D, H, W), device=fields.device, dtype=torch.float32)
-    call("smile_cwm_fuse_fwd", fields.data_ptr(), logits.data_ptr(), out.data_ptr(), B, F, D * H * W, _stream())
+    call("smile_cwm_fuse_fwd", fields.data_ptr(), logits.data_ptr(), out.data_ptr(), B, F, D * H * W, _stream(),
+         label=f"[f{F} {D}x{H}x{W}]")
     return out

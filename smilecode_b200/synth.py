@@ -46,3 +46,21 @@ def make_pair(shape: Sequence[int], batch: int = 1, seed: int = 24,
     moving = F.grid_sample(fixed, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
     moving = (moving + 0.01 * torch.randn(batch, 1, D, H, W, generator=g)).clamp_(0, 1) * mask
     return moving.contiguous(), fixed.contiguous()
+
+
+def randomize_weights(model: torch.nn.Module, seed: int = 1234) -> None:
+    """Non-degenerate decoder weights for benchmarks: the reference's default
+    init (proj.weight ~ N(0, 1e-5), rpb = 0) makes q, k ~ 0 and the flow ~ 5e-3 voxels, which would
+    exercise nothing.  proj.weight ~ N(0, 1/Cin), LayerNorm gain ~ U(0.25, 0.75), bias ~ N(0, 0.05),
+    rpb ~ N(0, 0.5); conv weights keep their default initialisation."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in sorted(model.named_parameters()):
+            if name.endswith("rpb"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.5)
+            elif name.endswith("proj.weight"):
+                p.copy_(torch.randn(p.shape, generator=g) / p.shape[1] ** 0.5)
+            elif name.endswith("norm.weight"):
+                p.copy_(torch.rand(p.shape, generator=g) * 0.5 + 0.25)
+            elif name.endswith("norm.bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)

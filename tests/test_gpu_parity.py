@@ -173,11 +173,16 @@ def test_encoder_golden():
 
 
 # ------------------------------------------------------------------ fused heads==1 level
-@pytest.mark.parametrize("shape", [(1, 6, 7, 9), (2, 8, 16, 32), (1, 12, 24, 64), (1, 5, 8, 66)])
-def test_fused_matches_unfused(ops, shape):
+@pytest.mark.parametrize("shape,sharp", [((1, 6, 7, 9), 1.0), ((2, 8, 16, 32), 1.0), ((1, 12, 24, 64), 1.0),
+                                         ((1, 5, 8, 66), 1.0), ((1, 40, 19, 80), 1.0), ((2, 3, 9, 36), 1.0),
+                                         ((1, 2, 2, 4), 1.0), ((1, 33, 8, 32), 1.0), ((1, 9, 12, 40), 40.0)])
+def test_fused_matches_unfused(ops, shape, sharp):
+    """Covers the TMA-staged marching kernel (W % 4 == 0: partial tiles in H and W, several depth
+    segments per CTA, batch > 1, saturated softmax -> |w| == 1 -> out-of-window gather path) and the
+    generic fused kernel (other W)."""
     B, D, H, W = shape
     g = torch.Generator().manual_seed(10)
-    q = torch.randn(B, D, H, W, 6, generator=g)
+    q = torch.randn(B, D, H, W, 6, generator=g) * sharp
     k = torch.randn(B, D, H, W, 6, generator=g)
     rpb = torch.randn(1, 3, 3, 3, generator=g) * 0.5
     # white-noise fields have O(1) voxel-to-voxel jumps, so the ~1e-6 error of w (approximate exp2)
@@ -189,7 +194,7 @@ def test_fused_matches_unfused(ops, shape):
         f_ref = post * (orc.warp_trilinear(flow, w) + w)
         m_ref = orc.warp_trilinear(mov, f_ref)
         f, m = ops.modet_fused(dev(q), dev(k), dev(rpb), dev(flow), dev(mov), 1.0, post)
-        assert (f.cpu() - f_ref).abs().max() <= 1e-4
+        assert rel_err(f.cpu(), f_ref) <= 1e-4          # north_star: 1e-4 relative fp32 (|f| reaches ~10 here)
         assert (m.cpu() - m_ref).abs().max() <= 1e-4
         f_only, none = ops.modet_fused(dev(q), dev(k), dev(rpb), dev(flow), None, 1.0, post)
         assert none is None and torch.equal(f_only, f)

@@ -11,6 +11,8 @@
 //     ("normalise on load"), and this layer's per-(b,c) sum / sum-of-squares are reduced
 //     warp -> CTA -> one fp64 atomicAdd per channel, so a ConvInsBlock costs one read of its
 //     input and one write of its raw output.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -199,9 +201,22 @@ static int launch_cfg(const float* in, const float* weight, const float* bias, f
   return check_launch("conv3d");
 }
 
+int launch_conv3d_tma(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
+                      double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
+                      cudaStream_t st, bool* handled);
+
 int launch_conv3d(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
                   double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
                   cudaStream_t st) {
+  {
+    static const bool no_tma = getenv("SMILE_CONV_NO_TMA") != nullptr;  // profiling knob: force the generic kernel
+    bool handled = false;
+    if (!no_tma) {
+      int rc = launch_conv3d_tma(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st,
+                                 &handled);
+      if (handled) return rc;
+    }
+  }
 #define SMILE_CONV(CO, V, TWL, NW, CIC) \
   return launch_cfg<CO, V, TWL, NW, CIC>(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st)
   const bool narrow = Cout <= 4;

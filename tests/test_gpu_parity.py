@@ -112,7 +112,11 @@ def test_projection_golden(ops, name):
 # ------------------------------------------------------------------ conv / IN / CWM / encoder
 @pytest.mark.parametrize("cin,cout,shape", [(1, 4, (6, 9, 40)), (4, 8, (5, 7, 33)), (8, 8, (8, 8, 32)),
                                             (6, 12, (4, 10, 14)), (16, 16, (5, 6, 7)), (24, 3, (3, 4, 5)),
-                                            (128, 128, (2, 3, 2)), (12, 2, (9, 5, 26))])
+                                            (128, 128, (2, 3, 2)), (12, 2, (9, 5, 26)),
+                                            # TMA-staged kernel: 32- and 16-wide tiles, partial tiles, odd channel counts
+                                            (8, 16, (9, 10, 64)), (16, 16, (5, 12, 80)), (4, 8, (10, 9, 160)),
+                                            (3, 5, (11, 7, 20)), (24, 48, (4, 6, 20)), (6, 12, (17, 3, 48)),
+                                            (32, 32, (8, 9, 40)), (1, 4, (3, 20, 96))])
 def test_conv3d_oracle(ops, cin, cout, shape):
     g = torch.Generator().manual_seed(8)
     x = torch.randn(2, cin, *shape, generator=g)

@@ -77,7 +77,7 @@ struct TCfg {
   static constexpr int OFF_W = 2 * IN_STRIDE;
   static constexpr int OFF_BAR = OFF_W + 2 * W_STRIDE;
   static constexpr int OFF_RED = OFF_BAR + 64;            // double [NW][CO][2]
-  static constexpr int OFF_MR = OFF_RED + NW * CO * 2 * 8;  // float [Cin][2] mean, rstd
+  static constexpr int OFF_MR = OFF_RED + NW * CO * 2 * 8;  // float [Cin][2] rstd, -mean * rstd
   static int smem_bytes(int Cin) { return OFF_MR + 2 * Cin * 4 + 16; }
 };
 
@@ -122,8 +122,9 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __rest
       const double s = in_stats[((long long)b * Cin + c) * 2], ss = in_stats[((long long)b * Cin + c) * 2 + 1];
       const double mean = s / (double)N;
       const double var = fmax(ss / (double)N - mean * mean, 0.0);
-      s_mr[2 * c] = (float)mean;
-      s_mr[2 * c + 1] = (float)(1.0 / sqrt(var + (double)eps));
+      const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+      s_mr[2 * c] = rstd;
+      s_mr[2 * c + 1] = -(float)mean * rstd;
     }
   }
 
@@ -172,26 +173,41 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __rest
     mbar_wait(bar0 + 8 * buf, (chunk >> 1) & 1);
     float* s_in = reinterpret_cast<float*>(smem + C::OFF_IN + buf * C::IN_STRIDE);
     if (NORM) {
-      // x <- LeakyReLU((x - mean_c) * rstd_c) on the in-volume part of the tile, float4 at a time
-      constexpr int ROW4 = TWP / 4;
-      constexpr int TOT4 = C::IN_ELEMS / 4;
-      for (int e = tid; e < TOT4; e += C::THREADS) {
-        const int x4 = e % ROW4;
-        int rr = e / ROW4;
-        const int y = rr % (TH + 2);
-        rr /= (TH + 2);
-        const int z = rr % (TD + 2);
-        const int c = rr / (TD + 2);
-        const int ci = chunk * CIC + c;
-        if (ci < Cin && z >= zlo && z < zhi && y >= ylo && y < yhi) {
-          const float mean = s_mr[2 * ci], rstd = s_mr[2 * ci + 1];
-          float4 v = reinterpret_cast<float4*>(s_in)[e];
-          const int x = 4 * x4;
-          v.x = (x >= xlo && x < xhi) ? lrelu01((v.x - mean) * rstd) : 0.f;
-          v.y = (x + 1 >= xlo && x + 1 < xhi) ? lrelu01((v.y - mean) * rstd) : 0.f;
-          v.z = (x + 2 >= xlo && x + 2 < xhi) ? lrelu01((v.z - mean) * rstd) : 0.f;
-          v.w = (x + 3 >= xlo && x + 3 < xhi) ? lrelu01((v.w - mean) * rstd) : 0.f;
-          reinterpret_cast<float4*>(s_in)[e] = v;
+      // x <- LeakyReLU((x - mean_c) * rstd_c) on the in-volume part of the tile.  A thread owns one
+      // float4 column of the tile (fixed x mask) and walks rows RPP at a time.
+      constexpr int R4 = TWP / 4;
+      constexpr int RPP = C::THREADS / R4;
+      constexpr int ROWS = CIC * (TD + 2) * (TH + 2);
+      const int tx4 = tid % R4, trow = tid / R4;
+      unsigned xm = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xm |= (unsigned)((4 * tx4 + i >= xlo) && (4 * tx4 + i < xhi)) << i;
+      if (trow < RPP) {
+        float4* s4 = reinterpret_cast<float4*>(s_in) + tx4;
+        for (int row = trow; row < ROWS; row += RPP) {
+          const int y = row % (TH + 2);
+          const int rz = row / (TH + 2);
+          const int z = rz % (TD + 2);
+          const int ci = chunk * CIC + rz / (TD + 2);
+          if (ci < Cin && z >= zlo && z < zhi && y >= ylo && y < yhi) {
+            const float2 mr = *reinterpret_cast<const float2*>(s_mr + 2 * ci);  // (rstd, -mean * rstd)
+            float4 v = s4[row * R4];
+            v.x = fmaf(v.x, mr.x, mr.y);
+            v.y = fmaf(v.y, mr.x, mr.y);
+            v.z = fmaf(v.z, mr.x, mr.y);
+            v.w = fmaf(v.w, mr.x, mr.y);
+            v.x = fmaxf(v.x, 0.1f * v.x);
+            v.y = fmaxf(v.y, 0.1f * v.y);
+            v.z = fmaxf(v.z, 0.1f * v.z);
+            v.w = fmaxf(v.w, 0.1f * v.w);
+            if (xm != 0xFu) {
+              if (!(xm & 1u)) v.x = 0.f;
+              if (!(xm & 2u)) v.y = 0.f;
+              if (!(xm & 4u)) v.z = 0.f;
+              if (!(xm & 8u)) v.w = 0.f;
+            }
+            s4[row * R4] = v;
+          }
         }
       }
     }

@@ -95,6 +95,32 @@ int smile_instnorm_lrelu_pool_fwd(const float* raw, const double* stats, float* 
 int smile_cwm_fuse_fwd(const float* fields, const float* logits, float* out, int B, int F, long long N,
                        smile_stream_t stream);
 
+/* a3  Twins of the reference's pybind pair (ModeT-cu/modet/modet.cpp:4-37; kernels modet_kernel.cu:17-381;
+ * Python caller ModeT-cu/functional.py:5-28).  Same tensors and layouts as the reference:
+ *   q      [B,heads,H,W,T,head_dim]        (already multiplied by scale, ModeT-cu/models.py:304)
+ *   kpad   [B,heads,H+2,W+2,T+2,head_dim]  (zero padded by the caller, models.py:305-306)
+ *   rpb    [heads,3,3,3] or NULL           (modet.cpp:13 substitutes zeros for None)
+ *   attn, d_attn [B,heads,H,W,T,27]        tap t = (ti*3 + tj)*3 + tk
+ * modet_fw:  attn[...,t] = <q, kpad[.. + (ti,tj,tk)]> + rpb[head,t]        (pre-softmax logits)
+ * modet_bw:  d_q, d_kpad (PADDED shape; the caller's pad-backward crops it), d_rpb (may be NULL when the
+ *            forward had no bias).  d_rpb is zeroed inside the call (the reference allocates torch::zeros). */
+int smile_modet_qkrpb_fwd(const float* q, const float* kpad, const float* rpb, float* attn, int B, int heads, int H,
+                          int W, int T, int head_dim, smile_stream_t stream);
+int smile_modet_qkrpb_bwd(const float* d_attn, const float* q, const float* kpad, float* d_q, float* d_kpad,
+                          float* d_rpb, int B, int heads, int H, int W, int T, int head_dim, smile_stream_t stream);
+
+/* a10 NCC_vxm.forward (ModeT/losses.py:43-95): out[0] = -mean(cc), cc from separable win^3 box sums of
+ * I, J, I^2, J^2, IJ with zero padding.  y_true, y_pred: [B,1,D,H,W].  work: device scratch of at least
+ * smile_ncc_vxm_work_bytes(B,D,H,W) bytes, 16-byte aligned. */
+long long smile_ncc_vxm_work_bytes(int B, int D, int H, int W);
+int smile_ncc_vxm_fwd(const float* y_true, const float* y_pred, float* out, void* work, int B, int D, int H, int W,
+                      int win, smile_stream_t stream);
+
+/* a10 Grad3d(penalty='l2').forward (ModeT/losses.py:16-31): out[0] = (mean(dD^2) + mean(dH^2) + mean(dW^2)) / 3 over
+ * forward differences of flow [B,C,D,H,W].  work: 3 doubles of device scratch (24 bytes, 16-byte aligned). */
+int smile_grad3d_l2_fwd(const float* flow, float* out, void* work, int B, int C, int D, int H, int W,
+                        smile_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

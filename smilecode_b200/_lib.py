@@ -23,6 +23,10 @@ SIGNATURES = {
     "smile_conv3d_fwd": [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P],
     "smile_instnorm_lrelu_pool_fwd": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P],
     "smile_cwm_fuse_fwd": [P, P, P, c_int, c_int, c_longlong, P],
+    "smile_modet_qkrpb_fwd": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "smile_modet_qkrpb_bwd": [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "smile_ncc_vxm_fwd": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
+    "smile_grad3d_l2_fwd": [P, P, P, c_int, c_int, c_int, c_int, c_int, P],
 }
 
 _lib = None
@@ -44,6 +48,8 @@ def lib() -> ctypes.CDLL:
         handle.smile_version.argtypes = []
         handle.smile_last_error.restype = c_char_p
         handle.smile_last_error.argtypes = []
+        handle.smile_ncc_vxm_work_bytes.restype = c_longlong
+        handle.smile_ncc_vxm_work_bytes.argtypes = [c_int, c_int, c_int, c_int]
         for name, argtypes in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype = c_int

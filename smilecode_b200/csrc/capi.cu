@@ -158,4 +158,53 @@ int smile_cwm_fuse_fwd(const float* fields, const float* logits, float* out, int
   return launch_cwm_fuse(fields, logits, out, B, F, N, (cudaStream_t)stream);
 }
 
+int smile_modet_qkrpb_fwd(const float* q, const float* kpad, const float* rpb, float* attn, int B, int heads, int H,
+                          int W, int T, int head_dim, smile_stream_t stream) {
+  REQUIRE_PTR(q);
+  REQUIRE_PTR(kpad);
+  REQUIRE_PTR(attn);
+  REQUIRE(rpb == nullptr || aligned16(rpb), "%s: rpb not 16-byte aligned", __func__);
+  REQUIRE(B > 0 && heads > 0 && H > 0 && W > 0 && T > 0 && head_dim > 0, "%s: bad sizes B=%d heads=%d H=%d W=%d T=%d hd=%d",
+          __func__, B, heads, H, W, T, head_dim);
+  return launch_qkrpb_fwd(q, kpad, rpb, attn, B, heads, H, W, T, head_dim, (cudaStream_t)stream);
+}
+
+int smile_modet_qkrpb_bwd(const float* d_attn, const float* q, const float* kpad, float* d_q, float* d_kpad,
+                          float* d_rpb, int B, int heads, int H, int W, int T, int head_dim, smile_stream_t stream) {
+  REQUIRE_PTR(d_attn);
+  REQUIRE_PTR(q);
+  REQUIRE_PTR(kpad);
+  REQUIRE_PTR(d_q);
+  REQUIRE_PTR(d_kpad);
+  REQUIRE(d_rpb == nullptr || aligned16(d_rpb), "%s: d_rpb not 16-byte aligned", __func__);
+  REQUIRE(B > 0 && heads > 0 && H > 0 && W > 0 && T > 0 && head_dim > 0, "%s: bad sizes B=%d heads=%d H=%d W=%d T=%d hd=%d",
+          __func__, B, heads, H, W, T, head_dim);
+  return launch_qkrpb_bwd(d_attn, q, kpad, d_q, d_kpad, d_rpb, B, heads, H, W, T, head_dim, (cudaStream_t)stream);
+}
+
+long long smile_ncc_vxm_work_bytes(int B, int D, int H, int W) {
+  return 10LL * B * D * H * W * (long long)sizeof(float) + 16;
+}
+
+int smile_ncc_vxm_fwd(const float* y_true, const float* y_pred, float* out, void* work, int B, int D, int H, int W,
+                      int win, smile_stream_t stream) {
+  REQUIRE_PTR(y_true);
+  REQUIRE_PTR(y_pred);
+  REQUIRE_PTR(out);
+  REQUIRE_PTR(work);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(win >= 1 && (win & 1) && win <= 63, "%s: win=%d must be odd and <= 63", __func__, win);
+  return launch_ncc_vxm(y_true, y_pred, out, reinterpret_cast<float*>(work), B, D, H, W, win, (cudaStream_t)stream);
+}
+
+int smile_grad3d_l2_fwd(const float* flow, float* out, void* work, int B, int C, int D, int H, int W,
+                        smile_stream_t stream) {
+  REQUIRE_PTR(flow);
+  REQUIRE_PTR(out);
+  REQUIRE_PTR(work);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(C > 0 && D > 1 && H > 1 && W > 1, "%s: needs C > 0 and every spatial dim > 1", __func__);
+  return launch_grad3d_l2(flow, out, reinterpret_cast<double*>(work), B, C, D, H, W, (cudaStream_t)stream);
+}
+
 }  // extern "C"

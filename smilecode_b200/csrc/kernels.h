@@ -29,4 +29,16 @@ int launch_in_finalize(const float* raw, const double* stats, float* out, float*
                        int W, float eps, cudaStream_t st);
 int launch_cwm_fuse(const float* fields, const float* logits, float* out, int B, int F, long long N, cudaStream_t st);
 
+
+// qkrpb.cu (a3: twins of the reference's modet_fw / modet_bw)
+int launch_qkrpb_fwd(const float* q, const float* kpad, const float* rpb, float* attn, int B, int heads, int H, int W,
+                     int T, int hd, cudaStream_t st);
+int launch_qkrpb_bwd(const float* d_attn, const float* q, const float* kpad, float* dq, float* dk, float* drpb, int B,
+                     int heads, int H, int W, int T, int hd, cudaStream_t st);
+
+// losses.cu (a10)
+int launch_ncc_vxm(const float* y_true, const float* y_pred, float* out, float* work, int B, int D, int H, int W, int win,
+                   cudaStream_t st);
+int launch_grad3d_l2(const float* flow, float* out, double* work, int B, int C, int D, int H, int W, cudaStream_t st);
+
 }  // namespace smile

@@ -193,3 +193,64 @@ def cwm_fuse(fields: Tensor, logits: Tensor) -> Tensor:
     call("smile_cwm_fuse_fwd", fields.data_ptr(), logits.data_ptr(), out.data_ptr(), B, F, D * H * W, _stream(),
          label=f"[f{F} {D}x{H}x{W}]")
     return out
+
+
+def modet_qkrpb_fwd(query: Tensor, key: Tensor, rpb: Optional[Tensor]) -> Tensor:
+    """Twin of the reference's `modet.modet_fw` (ModeT-cu/modet/modet.cpp:4-18): pre-softmax logits.
+    query [B,h,H,W,T,d], key [B,h,H+2,W+2,T+2,d] (zero padded), rpb [h,3,3,3] or None -> [B,h,H,W,T,27]."""
+    query = _chk(query, "query", 6)
+    key = _chk(key, "key", 6)
+    B, h, H, W, T, d = query.shape
+    if tuple(key.shape) != (B, h, H + 2, W + 2, T + 2, d):
+        raise SmileError(f"key must be the zero-padded [{B},{h},{H + 2},{W + 2},{T + 2},{d}], got {tuple(key.shape)}")
+    if rpb is not None:
+        rpb = _chk(rpb, "rpb", 4)
+        if tuple(rpb.shape) != (h, 3, 3, 3):
+            raise SmileError(f"rpb must be [{h},3,3,3], got {tuple(rpb.shape)}")
+    attn = torch.empty((B, h, H, W, T, 27), device=query.device, dtype=torch.float32)
+    call("smile_modet_qkrpb_fwd", query.data_ptr(), key.data_ptr(), _ptr(rpb), attn.data_ptr(), B, h, H, W, T, d, _stream(),
+         label=f"[h{h} {H}x{W}x{T}]")
+    return attn
+
+
+def modet_qkrpb_bwd(d_attn: Tensor, query: Tensor, key: Tensor, bias: bool):
+    """Twin of `modet.modet_bw` (modet.cpp:20-31): returns (d_query, d_key_padded, d_rpb or None)."""
+    d_attn = _chk(d_attn, "d_attn", 6)
+    query = _chk(query, "query", 6)
+    key = _chk(key, "key", 6)
+    B, h, H, W, T, d = query.shape
+    if tuple(d_attn.shape) != (B, h, H, W, T, 27) or tuple(key.shape) != (B, h, H + 2, W + 2, T + 2, d):
+        raise SmileError("modet_qkrpb_bwd: d_attn / query / key shapes disagree")
+    dq = torch.empty_like(query)
+    dk = torch.empty_like(key)
+    drpb = torch.empty((h, 3, 3, 3), device=query.device, dtype=torch.float32) if bias else None
+    call("smile_modet_qkrpb_bwd", d_attn.data_ptr(), query.data_ptr(), key.data_ptr(), dq.data_ptr(), dk.data_ptr(),
+         _ptr(drpb), B, h, H, W, T, d, _stream(), label=f"[h{h} {H}x{W}x{T}]")
+    return dq, dk, drpb
+
+
+def ncc_vxm(y_true: Tensor, y_pred: Tensor, win: int = 9) -> Tensor:
+    """NCC_vxm.forward (ModeT/losses.py:43-95): -mean local normalised cross-correlation, scalar tensor."""
+    y_true = _chk(y_true, "y_true", 5)
+    y_pred = _chk(y_pred, "y_pred", 5)
+    B, C, D, H, W = y_true.shape
+    if C != 1 or y_pred.shape != y_true.shape:
+        raise SmileError("ncc_vxm: y_true and y_pred must both be [B,1,D,H,W]")
+    from ._lib import lib
+    nbytes = lib().smile_ncc_vxm_work_bytes(B, D, H, W)
+    work = torch.empty(nbytes, device=y_true.device, dtype=torch.uint8)
+    out = torch.empty(1, device=y_true.device, dtype=torch.float32)
+    call("smile_ncc_vxm_fwd", y_true.data_ptr(), y_pred.data_ptr(), out.data_ptr(), work.data_ptr(), B, D, H, W, int(win),
+         _stream(), label=f"[{D}x{H}x{W}]")
+    return out[0]
+
+
+def grad3d_l2(flow: Tensor) -> Tensor:
+    """Grad3d(penalty='l2').forward (ModeT/losses.py:16-31), scalar tensor."""
+    flow = _chk(flow, "flow", 5)
+    B, C, D, H, W = flow.shape
+    work = torch.empty(4, device=flow.device, dtype=torch.float64)
+    out = torch.empty(1, device=flow.device, dtype=torch.float32)
+    call("smile_grad3d_l2_fwd", flow.data_ptr(), out.data_ptr(), work.data_ptr(), B, C, D, H, W, _stream(),
+         label=f"[{D}x{H}x{W}]")
+    return out[0]

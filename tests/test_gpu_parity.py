@@ -233,3 +233,79 @@ def test_errors_are_loud(ops):
         ops.warp3d(torch.zeros(1, 1, 4, 4, 4), torch.zeros(1, 3, 4, 4, 4))        # CPU tensors: no fallback
     with pytest.raises(Exception):
         ops.modet_attention(torch.zeros(1, 2, 2, 2, 6, device="cuda"), torch.zeros(1, 2, 2, 3, 6, device="cuda"), None, 1, 1.0)
+
+
+# ------------------------------------------------------------------ a3 twins of modet_fw / modet_bw
+def _qkrpb_ref(q, kp, rpb):
+    """Restatement of modet_kernel.cu:17-87: attn[..., t] = <q, kpad[.. + off(t)]> + rpb[head, t]."""
+    B, h, H, W, T, d = q.shape
+    outs = []
+    for t in range(27):
+        ti, tj, tk = t // 9, (t // 3) % 3, t % 3
+        lg = (q * kp[:, :, ti:ti + H, tj:tj + W, tk:tk + T]).sum(-1)
+        if rpb is not None:
+            lg = lg + rpb[:, ti, tj, tk].view(1, h, 1, 1, 1)
+        outs.append(lg)
+    return torch.stack(outs, -1)
+
+
+@pytest.mark.parametrize("shape,bias", [((2, 4, 5, 6, 7, 6), True), ((1, 1, 3, 3, 3, 6), True), ((1, 2, 2, 9, 4, 5), False),
+                                        ((1, 8, 10, 12, 10, 6), True)])
+def test_qkrpb_fwd_bwd_twins(ops, shape, bias):
+    B, h, H, W, T, d = shape
+    g = torch.Generator().manual_seed(12)
+    q = torch.randn(B, h, H, W, T, d, generator=g, requires_grad=True)
+    k = torch.randn(B, h, H, W, T, d, generator=g)
+    kp = torch.nn.functional.pad(k, (0, 0, 1, 1, 1, 1, 1, 1)).requires_grad_(True)
+    rpb = (torch.randn(h, 3, 3, 3, generator=g) * 0.5).requires_grad_(True) if bias else None
+    G = torch.randn(B, h, H, W, T, 27, generator=g)
+    ref = _qkrpb_ref(q, kp, rpb)
+    (ref * G).sum().backward()
+    with torch.no_grad():
+        attn = ops.modet_qkrpb_fwd(dev(q.detach()), dev(kp.detach()), dev(rpb.detach()) if bias else None)
+        dq, dk, drpb = ops.modet_qkrpb_bwd(dev(G), dev(q.detach()), dev(kp.detach()), bias)
+    assert (attn.cpu() - ref.detach()).abs().max() <= 5e-6
+    assert (dq.cpu() - q.grad).abs().max() <= 2e-5
+    assert (dk.cpu() - kp.grad).abs().max() <= 2e-5
+    if bias:
+        assert rel_err(drpb.cpu(), rpb.grad) <= 1e-5
+    else:
+        assert drpb is None
+
+
+def test_modetqkrpb_cu_autograd_dropin():
+    """smilecode_b200.functional.modetqkrpb_cu has the autograd contract of ModeT-cu/functional.py."""
+    from smilecode_b200.functional import modetqkrpb_cu
+    g = torch.Generator().manual_seed(13)
+    q = torch.randn(1, 2, 4, 5, 6, 6, generator=g)
+    k = torch.randn(1, 2, 4, 5, 6, 6, generator=g)
+    rpb = torch.randn(2, 3, 3, 3, generator=g)
+    qc, kc, rc = q.clone().requires_grad_(True), k.clone().requires_grad_(True), rpb.clone().requires_grad_(True)
+    ref = _qkrpb_ref(qc, torch.nn.functional.pad(kc, (0, 0, 1, 1, 1, 1, 1, 1)), rc).softmax(-1)
+    ref.pow(2).sum().backward()
+    qd, kd, rd = (dev(t).requires_grad_(True) for t in (q, k, rpb))
+    out = modetqkrpb_cu(qd, torch.nn.functional.pad(kd, (0, 0, 1, 1, 1, 1, 1, 1)), rd).softmax(-1)
+    out.pow(2).sum().backward()
+    assert (out.detach().cpu() - ref.detach()).abs().max() <= 1e-6
+    assert (qd.grad.cpu() - qc.grad).abs().max() <= 1e-5
+    assert (kd.grad.cpu() - kc.grad).abs().max() <= 1e-5
+    assert (rd.grad.cpu() - rc.grad).abs().max() <= 1e-5
+
+
+# ------------------------------------------------------------------ a10 losses
+def test_losses_golden(ops):
+    g = load_golden("losses_12x14x11")
+    ncc = ops.ncc_vxm(dev(g["a"]), dev(g["b"])).cpu()
+    grad = ops.grad3d_l2(dev(g["flow"])).cpu()
+    assert abs(float(ncc) - float(g["ncc"])) <= 1e-4 * max(1.0, abs(float(g["ncc"])))
+    assert abs(float(grad) - float(g["grad"])) <= 1e-5 * max(1.0, abs(float(g["grad"])))
+
+
+def test_losses_oracle_larger(ops):
+    from smilecode_b200.synth import make_pair
+    moving, fixed = make_pair((40, 48, 36), batch=2, seed=3)
+    ref = orc.ncc_vxm(fixed, moving)
+    out = ops.ncc_vxm(dev(fixed), dev(moving)).cpu()
+    assert abs(float(out) - float(ref)) <= 1e-4 * max(1.0, abs(float(ref)))
+    flow = torch.randn(2, 3, 17, 9, 23, generator=torch.Generator().manual_seed(2))
+    assert abs(float(ops.grad3d_l2(dev(flow)).cpu()) - float(orc.grad3d_l2(flow))) <= 1e-5

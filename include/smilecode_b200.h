@@ -74,6 +74,13 @@ int smile_modet_fused_fwd(const float* q, const float* k, const float* rpb, cons
 int smile_proj_ln_fwd(const float* feat, const float* weight, const float* bias, const float* gamma, const float* beta,
                       float* out, int B, int Cin, int C, long long N, float eps, smile_stream_t stream);
 
+/* a5+a7 fused (the pattern `M = transformer(M, flow); k = projblock(M)` of ModeT/models.py:388-389, 394-395,
+ * 400-401, 405-406): out = LayerNorm(Linear(SpatialTransformer(src, flow))) channels-last [B,D,H,W,C]
+ * without materialising the warped feature volume.  src: [B,Cin,D,H,W]; flow: [B,3,D,H,W]. */
+int smile_warp_proj_ln_fwd(const float* src, const float* flow, const float* weight, const float* bias,
+                           const float* gamma, const float* beta, float* out, int B, int Cin, int C, int D, int H,
+                           int W, float eps, smile_stream_t stream);
+
 /* a8/a4 Conv3d(kernel 3, stride 1, padding 1) (ModeT/models.py:127, 143, 253).
  *   in_stats  (fp64 [B*Cin][2] = sum, sum of squares of `in`) non-NULL: `in` is a raw conv output and
  *             InstanceNorm3d(eps)+LeakyReLU(0.1) of it is applied on load (models.py:148-150);

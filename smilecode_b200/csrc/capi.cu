@@ -123,6 +123,27 @@ int smile_proj_ln_fwd(const float* feat, const float* weight, const float* bias,
   return launch_proj_ln(feat, weight, bias, gamma, beta, out, B, Cin, C, N, eps, (cudaStream_t)stream);
 }
 
+int smile_warp_proj_ln_fwd(const float* src, const float* flow, const float* weight, const float* bias,
+                           const float* gamma, const float* beta, float* out, int B, int Cin, int C, int D, int H,
+                           int W, float eps, smile_stream_t stream) {
+  REQUIRE_PTR(src);
+  REQUIRE_PTR(flow);
+  REQUIRE_PTR(weight);
+  REQUIRE_PTR(bias);
+  REQUIRE_PTR(gamma);
+  REQUIRE_PTR(beta);
+  REQUIRE_PTR(out);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(Cin > 0 && C > 0, "%s: Cin=%d C=%d", __func__, Cin, C);
+  bool handled = false;
+  int rc = launch_warp_proj_ln(src, flow, weight, bias, gamma, beta, out, B, Cin, C, D, H, W, eps, (cudaStream_t)stream,
+                               &handled);
+  if (handled) return rc;
+  set_error("%s: no fused kernel for Cin=%d C=%d D=%d H=%d W=%d (use smile_warp3d_fwd + smile_proj_ln_fwd)", __func__, Cin,
+            C, D, H, W);
+  return SMILE_ERR_UNSUPPORTED;
+}
+
 int smile_conv3d_fwd(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
                      double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
                      smile_stream_t stream) {

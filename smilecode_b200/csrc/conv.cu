@@ -205,6 +205,10 @@ int launch_conv3d_tma(const float* in, const float* weight, const float* bias, f
                       double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
                       cudaStream_t st, bool* handled);
 
+int launch_conv3d_small(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
+                        double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
+                        cudaStream_t st, bool* handled);
+
 int launch_conv3d(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
                   double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
                   cudaStream_t st) {
@@ -214,6 +218,9 @@ int launch_conv3d(const float* in, const float* weight, const float* bias, float
     if (!no_tma) {
       int rc = launch_conv3d_tma(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st,
                                  &handled);
+      if (handled) return rc;
+      rc = launch_conv3d_small(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st,
+                               &handled);
       if (handled) return rc;
     }
   }

@@ -6,6 +6,9 @@ namespace smile {
 
 // warp.cu
 int launch_warp3d(const float* src, const float* flow, float* out, int B, int C, int D, int H, int W, cudaStream_t st);
+int launch_warp_proj_ln(const float* src, const float* flow, const float* weight, const float* bias, const float* gamma,
+                        const float* beta, float* out, int B, int Cin, int C, int D, int H, int W, float eps,
+                        cudaStream_t st, bool* handled);
 int launch_compose(const float* flow, const float* w, float* out, int B, int D, int H, int W, float post, cudaStream_t st);
 int launch_upsample2x(const float* x, float* out, int B, int C, int D, int H, int W, float pre, cudaStream_t st);
 

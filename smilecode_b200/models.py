@@ -147,6 +147,11 @@ class ProjectionLayer(nn.Module):
             raise NotImplementedError("ProjectionLayer: only norm=nn.LayerNorm is on the hot path")
         return ops.proj_ln(feat, self.proj.weight, self.proj.bias, self.norm.weight, self.norm.bias, self.norm.eps)
 
+    def of_warped(self, feat, flow):
+        """self(SpatialTransformer(feat, flow)) without materialising the warped volume (models.py:388-389)."""
+        return ops.warp_proj_ln(feat, flow, self.proj.weight, self.proj.bias, self.norm.weight, self.norm.bias,
+                                self.norm.eps)
+
 
 class CWM(nn.Module):
     """Competitive weighting module, reference ModeT/models.py:243-275."""
@@ -189,9 +194,10 @@ class ModeT(nn.Module):
                 setattr(self, f"cwm{level}", CWM(3 * heads, 3 * heads * 2))
         self.transformer = nn.ModuleList(SpatialTransformer([s // 2 ** i for s in inshape]) for i in range(4))
 
-    def _attend(self, level: int, feat_f, feat_m):
+    def _attend(self, level: int, feat_f, feat_m, flow):
+        """mdt(proj(F), proj(T(M, flow))) -- models.py:388-390."""
         pb, mdt = getattr(self, f"projblock{level}"), getattr(self, f"mdt{level}")
-        return mdt(pb(feat_f), pb(feat_m))
+        return mdt(pb(feat_f), pb.of_warped(feat_m, flow))
 
     def forward(self, moving, fixed):
         B = moving.shape[0]
@@ -202,18 +208,18 @@ class ModeT(nn.Module):
         # level 5 .. 3: multi-head attention -> CWM fusion (models.py:383-398)
         qk = self.projblock5(feats[4])                           # both volumes in one launch
         flow = self.cwm5(self.mdt5(qk[B:], qk[:B]))
-        w = self.cwm4(self._attend(4, Fx[3], ops.warp3d(M[3], flow)))
+        w = self.cwm4(self._attend(4, Fx[3], M[3], flow))
         flow = ops.flow_compose(ops.upsample2x(flow, 2.0), w)
-        w = self.cwm3(self._attend(3, Fx[2], ops.warp3d(M[2], flow)))
+        w = self.cwm3(self._attend(3, Fx[2], M[2], flow))
         flow = ops.flow_compose(ops.upsample2x(flow, 2.0), w)
 
         # level 2, 1: single head, attention + compose (+ final warp) fused (models.py:400-410)
         pb, mdt = self.projblock2, self.mdt2
-        f2, _ = ops.modet_fused(pb(Fx[1]), pb(ops.warp3d(M[1], flow)), mdt.rpb if mdt.use_rpb else None, flow, None,
+        f2, _ = ops.modet_fused(pb(Fx[1]), pb.of_warped(M[1], flow), mdt.rpb if mdt.use_rpb else None, flow, None,
                                 mdt.scale, postmul=2.0)
         flow = ops.upsample2x(f2)
         pb, mdt = self.projblock1, self.mdt1
-        flow, y_moved = ops.modet_fused(pb(Fx[0]), pb(ops.warp3d(M[0], flow)), mdt.rpb if mdt.use_rpb else None, flow,
+        flow, y_moved = ops.modet_fused(pb(Fx[0]), pb.of_warped(M[0], flow), mdt.rpb if mdt.use_rpb else None, flow,
                                         moving, mdt.scale, postmul=1.0)
         return y_moved, flow
 

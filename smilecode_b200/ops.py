@@ -144,6 +144,29 @@ def proj_ln(feat: Tensor, weight: Tensor, bias: Tensor, gamma: Tensor, beta: Ten
     return out
 
 
+FUSED_WARP_PROJ = {(8, 6), (16, 6), (32, 12), (64, 24)}   # (Cin, C) pairs compiled into smile_warp_proj_ln_fwd
+
+
+def warp_proj_ln(src: Tensor, flow: Tensor, weight: Tensor, bias: Tensor, gamma: Tensor, beta: Tensor,
+                 eps: float = IN_EPS) -> Tensor:
+    """ProjectionLayer(SpatialTransformer(src, flow)) (ModeT/models.py:388-389 pattern) -> [B,D,H,W,C]; one kernel
+    when (Cin, C) is one of the reference's decoder widths, otherwise warp3d followed by proj_ln."""
+    src = _chk(src, "src", 5)
+    flow = _chk(flow, "flow", 5)
+    weight = _chk(weight, "proj.weight", 2)
+    B, Cin, D, H, W = src.shape
+    C = weight.shape[0]
+    if (Cin, C) not in FUSED_WARP_PROJ or min(D, H, W) < 2:
+        return proj_ln(warp3d(src, flow), weight, bias, gamma, beta, eps)
+    if tuple(flow.shape) != (B, 3, D, H, W) or weight.shape[1] != Cin:
+        raise SmileError("warp_proj_ln: src / flow / weight shapes disagree")
+    bias, gamma, beta = _chk(bias, "proj.bias", 1), _chk(gamma, "norm.weight", 1), _chk(beta, "norm.bias", 1)
+    out = torch.empty((B, D, H, W, C), device=src.device, dtype=torch.float32)
+    call("smile_warp_proj_ln_fwd", src.data_ptr(), flow.data_ptr(), weight.data_ptr(), bias.data_ptr(), gamma.data_ptr(),
+         beta.data_ptr(), out.data_ptr(), B, Cin, C, D, H, W, float(eps), _stream(), label=f"[{Cin}->{C} {D}x{H}x{W}]")
+    return out
+
+
 def conv3d(x: Tensor, weight: Tensor, bias: Tensor, in_stats: Optional[Tensor] = None, want_stats: bool = False,
            act_out: bool = False, eps: float = IN_EPS) -> Tuple[Tensor, Optional[Tensor]]:
     """Conv3d(k=3, s=1, p=1) (ModeT/models.py:127, 143, 253).  With `in_stats` the input is a raw conv

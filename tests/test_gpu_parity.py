@@ -116,7 +116,9 @@ def test_projection_golden(ops, name):
                                             # TMA-staged kernel: 32- and 16-wide tiles, partial tiles, odd channel counts
                                             (8, 16, (9, 10, 64)), (16, 16, (5, 12, 80)), (4, 8, (10, 9, 160)),
                                             (3, 5, (11, 7, 20)), (24, 48, (4, 6, 20)), (6, 12, (17, 3, 48)),
-                                            (32, 32, (8, 9, 40)), (1, 4, (3, 20, 96))])
+                                            (32, 32, (8, 9, 40)), (1, 4, (3, 20, 96)),
+                                            # small-volume channel-lane kernel (W <= 16, Cout >= 16)
+                                            (64, 128, (10, 12, 10)), (7, 20, (3, 5, 13)), (16, 70, (2, 9, 4)), (5, 33, (6, 2, 16))])
 def test_conv3d_oracle(ops, cin, cout, shape):
     g = torch.Generator().manual_seed(8)
     x = torch.randn(2, cin, *shape, generator=g)
@@ -309,3 +311,19 @@ def test_losses_oracle_larger(ops):
     assert abs(float(out) - float(ref)) <= 1e-4 * max(1.0, abs(float(ref)))
     flow = torch.randn(2, 3, 17, 9, 23, generator=torch.Generator().manual_seed(2))
     assert abs(float(ops.grad3d_l2(dev(flow)).cpu()) - float(orc.grad3d_l2(flow))) <= 1e-5
+
+
+# ------------------------------------------------------------------ a5+a7 fused: proj(LN(warp))
+@pytest.mark.parametrize("cin,c,shape", [(8, 6, (9, 10, 33)), (16, 6, (5, 12, 20)), (32, 12, (4, 6, 10)), (64, 24, (3, 4, 5)),
+                                         (128, 48, (2, 3, 2))])
+def test_warp_proj_ln_matches_unfused_oracle(ops, cin, c, shape):
+    g = torch.Generator().manual_seed(14)
+    src = torch.randn(2, cin, *shape, generator=g)
+    flow = torch.randn(2, 3, *shape, generator=g) * 2
+    sd = {"p.proj.weight": torch.randn(c, cin, generator=g) / cin ** 0.5, "p.proj.bias": torch.randn(c, generator=g) * 0.1,
+          "p.norm.weight": torch.rand(c, generator=g) + 0.5, "p.norm.bias": torch.randn(c, generator=g) * 0.1}
+    ref = orc.projection(orc.warp_trilinear(src, flow), sd, "p")
+    out = ops.warp_proj_ln(dev(src), dev(flow), dev(sd["p.proj.weight"]), dev(sd["p.proj.bias"]), dev(sd["p.norm.weight"]),
+                           dev(sd["p.norm.bias"])).cpu()
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max() <= 2e-5

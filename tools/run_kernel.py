@@ -43,6 +43,16 @@ elif what in ("conv8", "conv4", "conv1"):
     st = torch.stack([x.double().sum((2, 3, 4)).flatten(), (x.double() ** 2).sum((2, 3, 4)).flatten()], 1).contiguous()
     fn = lambda: ops.conv3d(x, w, b, in_stats=st if cin > 1 else None, want_stats=True, act_out=cin == 1)
     nbytes = 2 * (cin + cout) * 4 * S[0] * S[1] * S[2]
+elif what in ("conv128", "conv64_20", "conv32_40", "conv16_80"):
+    cin, cout, shp = {"conv128": (128, 128, (10, 12, 10)), "conv64_20": (64, 64, (20, 24, 20)),
+                      "conv32_40": (32, 32, (40, 48, 40)), "conv16_80": (16, 16, (80, 96, 80))}[what]
+    x = torch.randn(2, cin, *shp, device=dev, generator=g)
+    w = torch.randn(cout, cin, 3, 3, 3, device=dev, generator=g) * 0.05
+    b = torch.randn(cout, device=dev, generator=g) * 0.1
+    st = torch.stack([x.double().sum((2, 3, 4)).flatten(), (x.double() ** 2).sum((2, 3, 4)).flatten()], 1).contiguous()
+    fn = lambda: ops.conv3d(x, w, b, in_stats=st, want_stats=True)
+    nbytes = 2 * (cin + cout) * 4 * shp[0] * shp[1] * shp[2]
+    print(f"GFLOP {2 * 27 * cin * cout * 2 * shp[0] * shp[1] * shp[2] / 1e9:.2f}")
 elif what == "warp8":
     src = torch.randn(1, 8, *S, device=dev, generator=g)
     flow = smooth_flow(S, 3.0)

@@ -327,3 +327,22 @@ def test_warp_proj_ln_matches_unfused_oracle(ops, cin, c, shape):
                            dev(sd["p.norm.bias"])).cpu()
     assert out.shape == ref.shape
     assert (out - ref).abs().max() <= 2e-5
+
+
+# ------------------------------------------------------------------ host-to-host pipeline
+def test_registration_pipeline_matches_direct_calls():
+    from smilecode_b200 import models
+    from smilecode_b200.pipeline import RegistrationPipeline
+    from smilecode_b200.synth import make_pair, randomize_weights
+    shape = (16, 32, 32)
+    model = models.ModeT(shape, head_dim=6, num_heads=[8, 4, 2, 1, 1], scale=1)
+    randomize_weights(model, seed=7)
+    model = model.cuda().eval()
+    pairs = [tuple(t.pin_memory() for t in make_pair(shape, batch=1, seed=50 + i)) for i in range(5)]
+    pipe = RegistrationPipeline(model, shape, depth=2)
+    outs = [(m.clone(), f.clone()) for m, f in pipe.run(pairs)]
+    assert len(outs) == len(pairs)
+    with torch.no_grad():
+        for (mv, fx), (moved_h, flow_h) in zip(pairs, outs):
+            moved, flow = model(mv.cuda(), fx.cuda())
+            assert torch.equal(moved.cpu(), moved_h) and torch.equal(flow.cpu(), flow_h)

@@ -26,8 +26,8 @@ def smooth_flow(shape, amp):
     return torch.nn.functional.interpolate(c, size=shape, mode="trilinear", align_corners=True).contiguous()
 
 
-if what in ("fused", "fused_l2"):
-    shp = S if what == "fused" else S2
+if what in ("fused", "fused_l2", "fused_nomov"):
+    shp = S2 if what == "fused_l2" else S
     q = torch.randn(1, *shp, 6, device=dev, generator=g)
     k = torch.randn(1, *shp, 6, device=dev, generator=g)
     rpb = torch.randn(1, 3, 3, 3, device=dev, generator=g) * 0.5
@@ -35,6 +35,15 @@ if what in ("fused", "fused_l2"):
     mov = torch.rand(1, 1, *shp, device=dev, generator=g) if what == "fused" else None
     fn = lambda: ops.modet_fused(q, k, rpb, flow, mov, 1.0, 1.0 if what == "fused" else 2.0)
     nbytes = (80 if what == "fused" else 72) * shp[0] * shp[1] * shp[2]
+    if what == "fused_nomov":
+        ops.modet_attention(q, k, rpb, 1, 1.0)
+        import time
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for a_, b_ in evs:
+            flush.zero_(); a_.record(); ops.modet_attention(q, k, rpb, 1, 1.0); b_.record()
+        torch.cuda.synchronize()
+        print("attention only:", min(a_.elapsed_time(b_) for a_, b_ in evs) * 1e3, "us")
 elif what in ("conv8", "conv4", "conv1"):
     cin, cout = {"conv8": (8, 8), "conv4": (4, 8), "conv1": (1, 4)}[what]
     x = torch.randn(2, cin, *S, device=dev, generator=g)

@@ -356,15 +356,53 @@ int launch_conv3d_tma(const float* in, const float* weight, const float* bias, f
   *handled = true;
 #define SMILE_TCONV(CO, V, TWL, NW, CIC) \
   return launch_tcfg<CO, V, TWL, NW, CIC>(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st)
-  if (W >= 64 || W == 32) {
-    if (Cout <= 4) SMILE_TCONV(4, 8, 32, 8, 2);
-    if (Cout <= 8) SMILE_TCONV(8, 8, 32, 8, 2);
-    SMILE_TCONV(16, 4, 32, 8, 2);
+  // Pick the largest register tile (V depths x CO channels per thread) that still yields about two
+  // waves of CTAs; small volumes (coarse pyramid levels, CWM) would otherwise run on a handful of SMs.
+  const int TWL = (W >= 64 || W == 32) ? 32 : 16;
+  const int TH = 8;
+  const long long plane_tiles = (long long)ceil_div(H, TH) * ceil_div(W, TWL) * B;
+  const long long want = 2LL * kNumSMs;
+  auto ctas = [&](int V, int CO) { return plane_tiles * ceil_div(D, V) * ceil_div(Cout, CO); };
+  const int co_cap = Cout <= 4 ? 4 : (Cout <= 8 ? 8 : 16);
+  // candidates in decreasing tile size: (V, CO)
+  const int cand[6][2] = {{4, 16}, {8, 8}, {4, 8}, {2, 16}, {2, 8}, {2, 4}};
+  int V = 2, CO = 4;
+  if (co_cap == 4) {
+    V = (ctas(8, 4) >= want) ? 8 : ((ctas(4, 4) >= want) ? 4 : 2);
+    CO = 4;
+  } else {
+    bool found = false;
+    for (int i = 0; i < 6 && !found; ++i) {
+      if (cand[i][1] > co_cap) continue;
+      if (ctas(cand[i][0], cand[i][1]) >= want) {
+        V = cand[i][0];
+        CO = cand[i][1];
+        found = true;
+      }
+    }
+    if (!found) {  // nothing reaches two waves: maximise the CTA count
+      V = 2;
+      CO = (co_cap >= 8 && ctas(2, 4) <= ctas(2, 8)) ? 8 : 4;
+    }
   }
-  // W in {16..60}: 16-wide tiles, two rows per warp
-  if (Cout <= 4) SMILE_TCONV(4, 8, 16, 4, 2);
-  if (Cout <= 8) SMILE_TCONV(8, 8, 16, 4, 2);
-  SMILE_TCONV(16, 4, 16, 4, 4);
+  if (TWL == 32) {
+    if (CO == 4 && V == 8) SMILE_TCONV(4, 8, 32, 8, 2);
+    if (CO == 4 && V == 4) SMILE_TCONV(4, 4, 32, 8, 4);
+    if (CO == 4) SMILE_TCONV(4, 2, 32, 8, 4);
+    if (CO == 8 && V == 8) SMILE_TCONV(8, 8, 32, 8, 2);
+    if (CO == 8 && V == 4) SMILE_TCONV(8, 4, 32, 8, 4);
+    if (CO == 8) SMILE_TCONV(8, 2, 32, 8, 4);
+    if (V == 4) SMILE_TCONV(16, 4, 32, 8, 2);
+    SMILE_TCONV(16, 2, 32, 8, 4);
+  }
+  if (CO == 4 && V == 8) SMILE_TCONV(4, 8, 16, 4, 2);
+  if (CO == 4 && V == 4) SMILE_TCONV(4, 4, 16, 4, 4);
+  if (CO == 4) SMILE_TCONV(4, 2, 16, 4, 4);
+  if (CO == 8 && V == 8) SMILE_TCONV(8, 8, 16, 4, 2);
+  if (CO == 8 && V == 4) SMILE_TCONV(8, 4, 16, 4, 4);
+  if (CO == 8) SMILE_TCONV(8, 2, 16, 4, 4);
+  if (V == 4) SMILE_TCONV(16, 4, 16, 4, 4);
+  SMILE_TCONV(16, 2, 16, 4, 4);
 #undef SMILE_TCONV
 }
 

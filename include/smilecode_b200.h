@@ -128,6 +128,38 @@ int smile_ncc_vxm_fwd(const float* y_true, const float* y_pred, float* out, void
 int smile_grad3d_l2_fwd(const float* flow, float* out, void* work, int B, int C, int D, int H, int W,
                         smile_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Backward entry points (training path).  The reference gets these from torch autograd over the library
+ * ops it calls; here each is a hand-written kernel.  Gradient outputs are caller-allocated
+ * and are (re)initialised inside the call where the kernel accumulates with atomics.
+ * ------------------------------------------------------------------------------------------------- */
+
+/* SpatialTransformer backward (ModeT/models.py:49-67 through grid_sample): g = d(loss)/d(out) [B,C,D,H,W];
+ * d_src [B,C,D,H,W] and/or d_flow [B,3,D,H,W]; either may be NULL. */
+int smile_warp3d_bwd(const float* g, const float* src, const float* flow, float* d_src, float* d_flow, int B, int C,
+                     int D, int H, int W, smile_stream_t stream);
+
+/* Adjoint of smile_upsample2x_fwd: g [B,C,2D,2H,2W] -> d_x [B,C,D,H,W] (premul folded in). */
+int smile_upsample2x_bwd(const float* g, float* d_x, int B, int C, int D, int H, int W, float premul,
+                         smile_stream_t stream);
+
+/* ModeTransformer backward (ModeT/models.py:308-334): g [B,3*heads,D,H,W]; q, k, d_q, d_k channels-last
+ * [B,D,H,W,heads*head_dim]; d_rpb [heads,3,3,3] or NULL; work: B*D*H*W*heads*27 floats of scratch (the
+ * d_logits, which the reference materialises as the gradient of its attn tensor). */
+int smile_modet_attn_bwd(const float* g, const float* q, const float* k, const float* rpb, float* d_q, float* d_k,
+                         float* d_rpb, float* work, int B, int D, int H, int W, int heads, int head_dim, float scale,
+                         smile_stream_t stream);
+
+/* ProjectionLayer backward (ModeT/models.py:238-241): g channels-last [B,N,C]; d_feat [B,Cin,N] (may be NULL);
+ * d_weight [C,Cin], d_bias, d_gamma, d_beta [C]. */
+int smile_proj_ln_bwd(const float* g, const float* feat, const float* weight, const float* bias, const float* gamma,
+                      float* d_feat, float* d_weight, float* d_bias, float* d_gamma, float* d_beta, int B, int Cin, int C,
+                      long long N, float eps, smile_stream_t stream);
+
+/* CWM tail backward (ModeT/models.py:268-275): g [B,3,N] -> d_fields [B,3F,N], d_logits [B,F,N]. */
+int smile_cwm_fuse_bwd(const float* g, const float* fields, const float* logits, float* d_fields, float* d_logits, int B,
+                       int F, long long N, smile_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

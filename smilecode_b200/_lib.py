@@ -28,6 +28,11 @@ SIGNATURES = {
     "smile_modet_qkrpb_bwd": [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "smile_ncc_vxm_fwd": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     "smile_grad3d_l2_fwd": [P, P, P, c_int, c_int, c_int, c_int, c_int, P],
+    "smile_warp3d_bwd": [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
+    "smile_upsample2x_bwd": [P, P, c_int, c_int, c_int, c_int, c_int, c_float, P],
+    "smile_modet_attn_bwd": [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P],
+    "smile_proj_ln_bwd": [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_longlong, c_float, P],
+    "smile_cwm_fuse_bwd": [P, P, P, P, P, c_int, c_int, c_longlong, P],
 }
 
 _lib = None

@@ -228,4 +228,67 @@ int smile_grad3d_l2_fwd(const float* flow, float* out, void* work, int B, int C,
   return launch_grad3d_l2(flow, out, reinterpret_cast<double*>(work), B, C, D, H, W, (cudaStream_t)stream);
 }
 
+int smile_warp3d_bwd(const float* g, const float* src, const float* flow, float* d_src, float* d_flow, int B, int C,
+                     int D, int H, int W, smile_stream_t stream) {
+  REQUIRE_PTR(g);
+  REQUIRE_PTR(src);
+  REQUIRE_PTR(flow);
+  REQUIRE(d_src != nullptr || d_flow != nullptr, "%s: both gradient outputs are NULL", __func__);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(C > 0, "%s: C=%d", __func__, C);
+  return launch_warp3d_bwd(g, src, flow, d_src, d_flow, B, C, D, H, W, (cudaStream_t)stream);
+}
+
+int smile_upsample2x_bwd(const float* g, float* d_x, int B, int C, int D, int H, int W, float premul,
+                         smile_stream_t stream) {
+  REQUIRE_PTR(g);
+  REQUIRE_PTR(d_x);
+  REQUIRE_VOL(B, 2 * D, 2 * H, 2 * W);
+  REQUIRE(C > 0, "%s: C=%d", __func__, C);
+  return launch_upsample2x_bwd(g, d_x, B, C, D, H, W, premul, (cudaStream_t)stream);
+}
+
+int smile_modet_attn_bwd(const float* g, const float* q, const float* k, const float* rpb, float* d_q, float* d_k,
+                         float* d_rpb, float* work, int B, int D, int H, int W, int heads, int head_dim, float scale,
+                         smile_stream_t stream) {
+  REQUIRE_PTR(g);
+  REQUIRE_PTR(q);
+  REQUIRE_PTR(k);
+  REQUIRE_PTR(d_q);
+  REQUIRE_PTR(d_k);
+  REQUIRE_PTR(work);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(heads > 0 && head_dim > 0 && heads <= 65535, "%s: heads=%d head_dim=%d", __func__, heads, head_dim);
+  return launch_modet_attn_bwd(g, q, k, rpb, d_q, d_k, d_rpb, work, B, D, H, W, heads, head_dim, scale,
+                               (cudaStream_t)stream);
+}
+
+int smile_proj_ln_bwd(const float* g, const float* feat, const float* weight, const float* bias, const float* gamma,
+                      float* d_feat, float* d_weight, float* d_bias, float* d_gamma, float* d_beta, int B, int Cin, int C,
+                      long long N, float eps, smile_stream_t stream) {
+  REQUIRE_PTR(g);
+  REQUIRE_PTR(feat);
+  REQUIRE_PTR(weight);
+  REQUIRE_PTR(bias);
+  REQUIRE_PTR(gamma);
+  REQUIRE_PTR(d_weight);
+  REQUIRE_PTR(d_bias);
+  REQUIRE_PTR(d_gamma);
+  REQUIRE_PTR(d_beta);
+  REQUIRE(B > 0 && Cin > 0 && C > 0 && N > 0 && N < (1LL << 31), "%s: bad sizes", __func__);
+  return launch_proj_ln_bwd(g, feat, weight, bias, gamma, d_feat, d_weight, d_bias, d_gamma, d_beta, B, Cin, C, N, eps,
+                            (cudaStream_t)stream);
+}
+
+int smile_cwm_fuse_bwd(const float* g, const float* fields, const float* logits, float* d_fields, float* d_logits, int B,
+                       int F, long long N, smile_stream_t stream) {
+  REQUIRE_PTR(g);
+  REQUIRE_PTR(fields);
+  REQUIRE_PTR(logits);
+  REQUIRE_PTR(d_fields);
+  REQUIRE_PTR(d_logits);
+  REQUIRE(B > 0 && F > 0 && N > 0, "%s: bad sizes", __func__);
+  return launch_cwm_fuse_bwd(g, fields, logits, d_fields, d_logits, B, F, N, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -44,4 +44,18 @@ int launch_ncc_vxm(const float* y_true, const float* y_pred, float* out, float* 
                    cudaStream_t st);
 int launch_grad3d_l2(const float* flow, float* out, double* work, int B, int C, int D, int H, int W, cudaStream_t st);
 
+
+// backward.cu (training path)
+int launch_warp3d_bwd(const float* g, const float* src, const float* flow, float* d_src, float* d_flow, int B, int C, int D,
+                      int H, int W, cudaStream_t st);
+int launch_upsample2x_bwd(const float* g, float* dx, int B, int C, int D, int H, int W, float pre, cudaStream_t st);
+int launch_modet_attn_bwd(const float* g, const float* q, const float* k, const float* rpb, float* dq, float* dk,
+                          float* drpb, float* dl_work, int B, int D, int H, int W, int heads, int hd, float scale,
+                          cudaStream_t st);
+int launch_proj_ln_bwd(const float* gout, const float* feat, const float* weight, const float* bias, const float* gamma,
+                       float* dfeat, float* dweight, float* dbias, float* dgamma, float* dbeta, int B, int Cin, int C,
+                       long long N, float eps, cudaStream_t st);
+int launch_cwm_fuse_bwd(const float* g, const float* fields, const float* logits, float* dfields, float* dlogits, int B,
+                        int F, long long N, cudaStream_t st);
+
 }  // namespace smile

@@ -277,3 +277,64 @@ def grad3d_l2(flow: Tensor) -> Tensor:
     call("smile_grad3d_l2_fwd", flow.data_ptr(), out.data_ptr(), work.data_ptr(), B, C, D, H, W, _stream(),
          label=f"[{D}x{H}x{W}]")
     return out[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# backward operators (training path); thin wrappers like the forward ones
+# ------------------------------------------------------------------------------------------------
+def warp3d_bwd(g: Tensor, src: Tensor, flow: Tensor, need_src: bool = True, need_flow: bool = True):
+    """Gradients of warp3d w.r.t. src and flow (SpatialTransformer backward)."""
+    g, src, flow = _chk(g, "g", 5), _chk(src, "src", 5), _chk(flow, "flow", 5)
+    B, C, D, H, W = src.shape
+    d_src = torch.empty_like(src) if need_src else None
+    d_flow = torch.empty_like(flow) if need_flow else None
+    call("smile_warp3d_bwd", g.data_ptr(), src.data_ptr(), flow.data_ptr(), _ptr(d_src), _ptr(d_flow), B, C, D, H, W,
+         _stream(), label=f"[c{C} {D}x{H}x{W}]")
+    return d_src, d_flow
+
+
+def upsample2x_bwd(g: Tensor, premul: float = 1.0) -> Tensor:
+    g = _chk(g, "g", 5)
+    B, C, OD, OH, OW = g.shape
+    dx = torch.empty((B, C, OD // 2, OH // 2, OW // 2), device=g.device, dtype=torch.float32)
+    call("smile_upsample2x_bwd", g.data_ptr(), dx.data_ptr(), B, C, OD // 2, OH // 2, OW // 2, float(premul), _stream(),
+         label=f"[c{C} {OD // 2}x{OH // 2}x{OW // 2}]")
+    return dx
+
+
+def modet_attention_bwd(g: Tensor, q: Tensor, k: Tensor, rpb: Optional[Tensor], heads: int, scale: float):
+    g, q, k = _chk(g, "g", 5), _chk(q, "q", 5), _chk(k, "k", 5)
+    B, D, H, W, C = q.shape
+    if rpb is not None:
+        rpb = _chk(rpb, "rpb", 4)
+    dq, dk = torch.empty_like(q), torch.empty_like(k)
+    drpb = torch.empty((heads, 3, 3, 3), device=q.device, dtype=torch.float32) if rpb is not None else None
+    work = torch.empty(B * D * H * W * heads * 27, device=q.device, dtype=torch.float32)
+    call("smile_modet_attn_bwd", g.data_ptr(), q.data_ptr(), k.data_ptr(), _ptr(rpb), dq.data_ptr(), dk.data_ptr(),
+         _ptr(drpb), work.data_ptr(), B, D, H, W, heads, C // heads, float(scale), _stream(), label=f"[h{heads} {D}x{H}x{W}]")
+    return dq, dk, drpb
+
+
+def proj_ln_bwd(g: Tensor, feat: Tensor, weight: Tensor, bias: Tensor, gamma: Tensor, eps: float = IN_EPS,
+                need_feat: bool = True):
+    g, feat, weight = _chk(g, "g", 5), _chk(feat, "feat", 5), _chk(weight, "proj.weight", 2)
+    bias, gamma = _chk(bias, "proj.bias", 1), _chk(gamma, "norm.weight", 1)
+    B, Cin, D, H, W = feat.shape
+    C = weight.shape[0]
+    dfeat = torch.empty_like(feat) if need_feat else None
+    dw, db = torch.empty_like(weight), torch.empty_like(bias)
+    dg, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
+    call("smile_proj_ln_bwd", g.data_ptr(), feat.data_ptr(), weight.data_ptr(), bias.data_ptr(), gamma.data_ptr(),
+         _ptr(dfeat), dw.data_ptr(), db.data_ptr(), dg.data_ptr(), dbeta.data_ptr(), B, Cin, C, D * H * W, float(eps),
+         _stream(), label=f"[{Cin}->{C} {D}x{H}x{W}]")
+    return dfeat, dw, db, dg, dbeta
+
+
+def cwm_fuse_bwd(g: Tensor, fields: Tensor, logits: Tensor):
+    g, fields, logits = _chk(g, "g", 5), _chk(fields, "fields", 5), _chk(logits, "logits", 5)
+    B, F = logits.shape[0], logits.shape[1]
+    N = logits.shape[2] * logits.shape[3] * logits.shape[4]
+    dfields, dlogits = torch.empty_like(fields), torch.empty_like(logits)
+    call("smile_cwm_fuse_bwd", g.data_ptr(), fields.data_ptr(), logits.data_ptr(), dfields.data_ptr(), dlogits.data_ptr(),
+         B, F, N, _stream(), label=f"[f{F}]")
+    return dfields, dlogits

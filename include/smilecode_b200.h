@@ -160,6 +160,34 @@ int smile_proj_ln_bwd(const float* g, const float* feat, const float* weight, co
 int smile_cwm_fuse_bwd(const float* g, const float* fields, const float* logits, float* d_fields, float* d_logits, int B,
                        int F, long long N, smile_stream_t stream);
 
+/* Conv3d backward pieces (nn.Conv3d k=3 s=1 p=1; ModeT/models.py:127, 143, 253).
+ *   data gradient:   d_in = smile_conv3d_fwd(d_out, wT, zero bias) with wT = smile_conv3d_flip_weights(w):
+ *                    wT[ci][co][26-t] = w[co][ci][t]                       (wT: [Cin,Cout,3,3,3])
+ *   weight gradient: d_w[co][ci][t] = sum_{b,v} d_out[b,co,v] * in[b,ci,v+off(t)], d_b[co] = sum d_out (d_b may be NULL) */
+int smile_conv3d_flip_weights(const float* w, float* wT, int Cout, int Cin, smile_stream_t stream);
+int smile_conv3d_wgrad(const float* in, const float* d_out, float* d_w, float* d_b, int B, int Cin, int Cout, int D, int H,
+                       int W, smile_stream_t stream);
+
+/* InstanceNorm3d + LeakyReLU(0.1) backward (models.py:148-150): act = lrelu(IN(raw)); given d_act, act and the forward
+ * fp64 (sum, sumsq) of raw, writes d_raw.  mode 0: IN + LeakyReLU; mode 1: LeakyReLU only (ConvBlock, models.py:131-132;
+ * stats / work may be NULL).  work: B*C*2 doubles of scratch.  d_raw may alias d_act. */
+int smile_in_lrelu_bwd(const float* d_act, const float* act, const double* fwd_stats, void* work, float* d_raw, int B, int C,
+                       long long N, float eps, int mode, smile_stream_t stream);
+
+/* AvgPool3d(2) backward, accumulated: d_full[b,c,d,h,w] += d_pooled[b,c,d/2,h/2,w/2] / 8 (models.py:198). */
+int smile_avgpool2_bwd_add(const float* d_pooled, float* d_full, int B, int C, int D, int H, int W, smile_stream_t stream);
+
+/* Loss backward (ModeT/losses.py).  gscale: device pointer to the upstream scalar gradient (NULL = 1).
+ * NCC_vxm: gradient w.r.t. the FIRST argument (train.py:126 passes the warped image there); work as in the forward. */
+int smile_ncc_vxm_bwd(const float* y_true, const float* y_pred, float* d_true, void* work, const float* gscale, int B, int D,
+                      int H, int W, int win, smile_stream_t stream);
+int smile_grad3d_l2_bwd(const float* flow, float* d_flow, const float* gscale, int B, int C, int D, int H, int W,
+                        smile_stream_t stream);
+
+/* torch.optim.Adam(amsgrad=True, weight_decay=0) update of one flat fp32 buffer (ModeT/train.py:101); step counts from 1. */
+int smile_adam_amsgrad_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq,
+                            long long n, float lr, float beta1, float beta2, float eps, int step, smile_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,13 @@ SIGNATURES = {
     "smile_modet_attn_bwd": [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P],
     "smile_proj_ln_bwd": [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_longlong, c_float, P],
     "smile_cwm_fuse_bwd": [P, P, P, P, P, c_int, c_int, c_longlong, P],
+    "smile_conv3d_flip_weights": [P, P, c_int, c_int, P],
+    "smile_conv3d_wgrad": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "smile_in_lrelu_bwd": [P, P, P, P, P, c_int, c_int, c_longlong, c_float, c_int, P],
+    "smile_avgpool2_bwd_add": [P, P, c_int, c_int, c_int, c_int, c_int, P],
+    "smile_ncc_vxm_bwd": [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
+    "smile_grad3d_l2_bwd": [P, P, P, c_int, c_int, c_int, c_int, c_int, P],
+    "smile_adam_amsgrad_step": [P, P, P, P, P, c_longlong, c_float, c_float, c_float, c_float, c_int, P],
 }
 
 _lib = None

@@ -291,4 +291,73 @@ int smile_cwm_fuse_bwd(const float* g, const float* fields, const float* logits,
   return launch_cwm_fuse_bwd(g, fields, logits, d_fields, d_logits, B, F, N, (cudaStream_t)stream);
 }
 
+int smile_conv3d_flip_weights(const float* w, float* wT, int Cout, int Cin, smile_stream_t stream) {
+  REQUIRE_PTR(w);
+  REQUIRE_PTR(wT);
+  REQUIRE(Cout > 0 && Cin > 0 && w != wT, "%s: bad arguments", __func__);
+  return launch_conv3d_flip_weights(w, wT, Cout, Cin, (cudaStream_t)stream);
+}
+
+int smile_conv3d_wgrad(const float* in, const float* d_out, float* d_w, float* d_b, int B, int Cin, int Cout, int D, int H,
+                       int W, smile_stream_t stream) {
+  REQUIRE_PTR(in);
+  REQUIRE_PTR(d_out);
+  REQUIRE_PTR(d_w);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(Cin > 0 && Cout > 0 && B <= 65535, "%s: bad sizes", __func__);
+  return launch_conv3d_wgrad(in, d_out, d_w, d_b, B, Cin, Cout, D, H, W, (cudaStream_t)stream);
+}
+
+int smile_in_lrelu_bwd(const float* d_act, const float* act, const double* fwd_stats, void* work, float* d_raw, int B, int C,
+                       long long N, float eps, int mode, smile_stream_t stream) {
+  REQUIRE_PTR(d_act);
+  REQUIRE_PTR(act);
+  REQUIRE_PTR(d_raw);
+  REQUIRE(mode == 1 || (fwd_stats != nullptr && work != nullptr), "%s: mode 0 needs fwd_stats and work", __func__);
+  REQUIRE(B > 0 && C > 0 && N > 0 && (long long)B * C <= 65535, "%s: bad sizes", __func__);
+  return launch_in_lrelu_bwd(d_act, act, fwd_stats, reinterpret_cast<double*>(work), d_raw, B, C, N, eps, mode,
+                             (cudaStream_t)stream);
+}
+
+int smile_avgpool2_bwd_add(const float* d_pooled, float* d_full, int B, int C, int D, int H, int W, smile_stream_t stream) {
+  REQUIRE_PTR(d_pooled);
+  REQUIRE_PTR(d_full);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(C > 0 && (long long)B * C <= 65535, "%s: bad sizes", __func__);
+  return launch_pool_bwd_add(d_pooled, d_full, B, C, D, H, W, (cudaStream_t)stream);
+}
+
+int smile_ncc_vxm_bwd(const float* y_true, const float* y_pred, float* d_true, void* work, const float* gscale, int B, int D,
+                      int H, int W, int win, smile_stream_t stream) {
+  REQUIRE_PTR(y_true);
+  REQUIRE_PTR(y_pred);
+  REQUIRE_PTR(d_true);
+  REQUIRE_PTR(work);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(win >= 1 && (win & 1) && win <= 63, "%s: win=%d must be odd and <= 63", __func__, win);
+  return launch_ncc_vxm_bwd(y_true, y_pred, d_true, reinterpret_cast<float*>(work), gscale, B, D, H, W, win,
+                            (cudaStream_t)stream);
+}
+
+int smile_grad3d_l2_bwd(const float* flow, float* d_flow, const float* gscale, int B, int C, int D, int H, int W,
+                        smile_stream_t stream) {
+  REQUIRE_PTR(flow);
+  REQUIRE_PTR(d_flow);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(C > 0 && D > 1 && H > 1 && W > 1, "%s: needs C > 0 and every spatial dim > 1", __func__);
+  return launch_grad3d_l2_bwd(flow, d_flow, gscale, B, C, D, H, W, (cudaStream_t)stream);
+}
+
+int smile_adam_amsgrad_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq,
+                            long long n, float lr, float beta1, float beta2, float eps, int step, smile_stream_t stream) {
+  REQUIRE_PTR(param);
+  REQUIRE_PTR(grad);
+  REQUIRE_PTR(exp_avg);
+  REQUIRE_PTR(exp_avg_sq);
+  REQUIRE_PTR(max_exp_avg_sq);
+  REQUIRE(n > 0 && step >= 1, "%s: n=%lld step=%d", __func__, n, step);
+  return launch_adam_amsgrad(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n, lr, beta1, beta2, eps, step,
+                             (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -58,4 +58,19 @@ int launch_proj_ln_bwd(const float* gout, const float* feat, const float* weight
 int launch_cwm_fuse_bwd(const float* g, const float* fields, const float* logits, float* dfields, float* dlogits, int B,
                         int F, long long N, cudaStream_t st);
 
+
+// backward_conv.cu
+int launch_conv3d_flip_weights(const float* w, float* wT, int Cout, int Cin, cudaStream_t st);
+int launch_conv3d_wgrad(const float* x, const float* dy, float* dw, float* db, int B, int Cin, int Cout, int D, int H,
+                        int W, cudaStream_t st);
+int launch_in_lrelu_bwd(const float* da, const float* act, const double* fwd_stats, double* sums_work, float* dy, int B,
+                        int C, long long N, float eps, int mode, cudaStream_t st);
+int launch_pool_bwd_add(const float* dpooled, float* dfull, int B, int C, int D, int H, int W, cudaStream_t st);
+int launch_grad3d_l2_bwd(const float* flow, float* dflow, const float* gscale, int B, int C, int D, int H, int W,
+                         cudaStream_t st);
+int launch_ncc_vxm_bwd(const float* y_true, const float* y_pred, float* d_true, float* work, const float* gscale, int B,
+                       int D, int H, int W, int win, cudaStream_t st);
+int launch_adam_amsgrad(float* p, const float* g, float* m, float* v, float* vmax, long long n, float lr, float b1,
+                        float b2, float eps, int step, cudaStream_t st);
+
 }  // namespace smile

@@ -338,3 +338,71 @@ def cwm_fuse_bwd(g: Tensor, fields: Tensor, logits: Tensor):
     call("smile_cwm_fuse_bwd", g.data_ptr(), fields.data_ptr(), logits.data_ptr(), dfields.data_ptr(), dlogits.data_ptr(),
          B, F, N, _stream(), label=f"[f{F}]")
     return dfields, dlogits
+
+
+def conv3d_bwd(g: Tensor, x: Tensor, weight: Tensor, need_x: bool = True, need_bias: bool = True):
+    """Gradients of conv3d (k=3, s=1, p=1): d_x through the forward kernel with flipped weights, d_weight, d_bias."""
+    g, x, weight = _chk(g, "g", 5), _chk(x, "x", 5), _chk(weight, "weight", 5)
+    B, Cin, D, H, W = x.shape
+    Cout = weight.shape[0]
+    dx = None
+    if need_x:
+        wT = torch.empty((Cin, Cout, 3, 3, 3), device=x.device, dtype=torch.float32)
+        call("smile_conv3d_flip_weights", weight.data_ptr(), wT.data_ptr(), Cout, Cin, _stream())
+        zero_b = torch.zeros(Cin, device=x.device, dtype=torch.float32)
+        dx, _ = conv3d(g, wT, zero_b)
+    dw = torch.empty_like(weight)
+    db = torch.empty(Cout, device=x.device, dtype=torch.float32) if need_bias else None
+    call("smile_conv3d_wgrad", x.data_ptr(), g.data_ptr(), dw.data_ptr(), _ptr(db), B, Cin, Cout, D, H, W, _stream(),
+         label=f"[{Cin}->{Cout} {D}x{H}x{W}]")
+    return dx, dw, db
+
+
+def in_lrelu_bwd(d_act: Tensor, act: Tensor, stats: Optional[Tensor], mode: int = 0, eps: float = IN_EPS) -> Tensor:
+    """d_raw of act = LeakyReLU(InstanceNorm(raw)) (mode 0) or act = LeakyReLU(raw) (mode 1)."""
+    d_act, act = _chk(d_act, "d_act", 5), _chk(act, "act", 5)
+    B, C, D, H, W = act.shape
+    work = torch.empty((B * C, 2), device=act.device, dtype=torch.float64) if mode == 0 else None
+    if mode == 0:
+        stats = _chk(stats, "stats", 2, torch.float64)
+    d_raw = torch.empty_like(act)
+    call("smile_in_lrelu_bwd", d_act.data_ptr(), act.data_ptr(), _ptr(stats) if mode == 0 else None, _ptr(work),
+         d_raw.data_ptr(), B, C, D * H * W, float(eps), int(mode), _stream(), label=f"[c{C} {D}x{H}x{W}]")
+    return d_raw
+
+
+def avgpool2_bwd_add(d_pooled: Tensor, d_full: Tensor) -> Tensor:
+    """d_full += AvgPool3d(2) backward of d_pooled (in place)."""
+    d_pooled, d_full = _chk(d_pooled, "d_pooled", 5), _chk(d_full, "d_full", 5)
+    B, C, D, H, W = d_full.shape
+    call("smile_avgpool2_bwd_add", d_pooled.data_ptr(), d_full.data_ptr(), B, C, D, H, W, _stream())
+    return d_full
+
+
+def ncc_vxm_bwd(y_true: Tensor, y_pred: Tensor, gscale: Optional[Tensor], win: int = 9) -> Tensor:
+    y_true, y_pred = _chk(y_true, "y_true", 5), _chk(y_pred, "y_pred", 5)
+    B, C, D, H, W = y_true.shape
+    from ._lib import lib
+    work = torch.empty(lib().smile_ncc_vxm_work_bytes(B, D, H, W), device=y_true.device, dtype=torch.uint8)
+    d_true = torch.empty_like(y_true)
+    call("smile_ncc_vxm_bwd", y_true.data_ptr(), y_pred.data_ptr(), d_true.data_ptr(), work.data_ptr(), _ptr(gscale), B, D,
+         H, W, int(win), _stream())
+    return d_true
+
+
+def grad3d_l2_bwd(flow: Tensor, gscale: Optional[Tensor]) -> Tensor:
+    flow = _chk(flow, "flow", 5)
+    B, C, D, H, W = flow.shape
+    d_flow = torch.empty_like(flow)
+    call("smile_grad3d_l2_bwd", flow.data_ptr(), d_flow.data_ptr(), _ptr(gscale), B, C, D, H, W, _stream())
+    return d_flow
+
+
+def adam_amsgrad_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, max_exp_avg_sq: Tensor, lr: float,
+                      beta1: float, beta2: float, eps: float, step: int) -> None:
+    """In-place torch.optim.Adam(amsgrad=True) update of a flat fp32 buffer."""
+    for t in (param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise SmileError("adam_amsgrad_step: all buffers must be contiguous fp32 CUDA tensors")
+    call("smile_adam_amsgrad_step", param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+         max_exp_avg_sq.data_ptr(), param.numel(), float(lr), float(beta1), float(beta2), float(eps), int(step), _stream())

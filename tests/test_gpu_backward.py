@@ -100,3 +100,80 @@ def test_cwm_fuse_backward(F, shape):
     (CwmFuse.apply(ud, ld) * dev(G)).sum().backward()
     assert rel(ud.grad.cpu(), ur.grad) <= 1e-5
     assert rel(ld.grad.cpu(), lr.grad) <= 1e-5
+
+
+@pytest.mark.parametrize("cin,cout,shape,pool", [(4, 8, (6, 8, 34), True), (1, 4, (5, 6, 7), False), (16, 16, (4, 6, 20), True),
+                                                 (64, 128, (4, 6, 10), False), (6, 12, (3, 5, 33), False)])
+def test_conv_in_lrelu_backward(cin, cout, shape, pool):
+    from smilecode_b200.autograd import ConvINLReLU
+    g = torch.Generator().manual_seed(25)
+    x = torch.randn(2, cin, *shape, generator=g)
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    G = torch.randn(2, cout, *shape, generator=g)
+    Gp = torch.randn(2, cout, *[s // 2 for s in shape], generator=g)
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    act = orc.lrelu(orc.instance_norm(orc.conv3(xr, wr, br)))
+    loss = (act * G).sum()
+    if pool:
+        loss = loss + (torch.nn.functional.avg_pool3d(act, 2) * Gp).sum()
+    loss.backward()
+    xd, wd, bd = (dev(t).requires_grad_(True) for t in (x, w, b))
+    if pool:
+        a, p = ConvINLReLU.apply(xd, wd, bd, True)
+        ((a * dev(G)).sum() + (p * dev(Gp)).sum()).backward()
+    else:
+        (ConvINLReLU.apply(xd, wd, bd, False) * dev(G)).sum().backward()
+    assert rel(xd.grad.cpu(), xr.grad) <= 1e-4
+    assert rel(wd.grad.cpu(), wr.grad) <= 1e-4
+    assert bd.grad.abs().max() <= 1e-3 * wd.grad.abs().max()          # bias before InstanceNorm has zero gradient
+
+
+def test_conv_lrelu_and_plain_conv_backward():
+    from smilecode_b200.autograd import Conv, ConvLReLU
+    g = torch.Generator().manual_seed(26)
+    x = torch.randn(2, 3, 5, 7, 36, generator=g)
+    w = torch.randn(5, 3, 3, 3, 3, generator=g) * 0.2
+    b = torch.randn(5, generator=g) * 0.1
+    G = torch.randn(2, 5, 5, 7, 36, generator=g)
+    for fn, ref in ((ConvLReLU, lambda a, c, e: orc.lrelu(orc.conv3(a, c, e))), (Conv, orc.conv3)):
+        xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+        (ref(xr, wr, br) * G).sum().backward()
+        xd, wd, bd = (dev(t).requires_grad_(True) for t in (x, w, b))
+        (fn.apply(xd, wd, bd) * dev(G)).sum().backward()
+        assert rel(xd.grad.cpu(), xr.grad) <= 2e-5
+        assert rel(wd.grad.cpu(), wr.grad) <= 2e-5
+        assert rel(bd.grad.cpu(), br.grad) <= 2e-5
+
+
+def test_losses_backward():
+    from smilecode_b200.autograd import Grad3dLoss, NCCLoss
+    from smilecode_b200.synth import make_pair
+    moving, fixed = make_pair((20, 24, 18), batch=2, seed=5)
+    mr = moving.clone().requires_grad_(True)
+    (3.0 * orc.ncc_vxm(mr, fixed)).backward()
+    md = dev(moving).requires_grad_(True)
+    (3.0 * NCCLoss.apply(md, dev(fixed), 9)).backward()
+    assert rel(md.grad.cpu(), mr.grad) <= 2e-3           # cc has cancellation in flat regions (var ~ 1e-5)
+    flow = torch.randn(2, 3, 7, 9, 11, generator=torch.Generator().manual_seed(6))
+    fr = flow.clone().requires_grad_(True)
+    (0.5 * orc.grad3d_l2(fr)).backward()
+    fd = dev(flow).requires_grad_(True)
+    (0.5 * Grad3dLoss.apply(fd)).backward()
+    assert rel(fd.grad.cpu(), fr.grad) <= 1e-5
+
+
+def test_adam_amsgrad_matches_torch():
+    from smilecode_b200 import ops
+    g = torch.Generator().manual_seed(27)
+    p0 = torch.randn(1000, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-2, amsgrad=True)
+    p = dev(p0)
+    m, v, vm = torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 6):
+        grad = torch.randn(1000, generator=g) * (0.1 if step == 4 else 1.0)
+        ref.grad = grad.clone()
+        opt.step()
+        ops.adam_amsgrad_step(p, dev(grad), m, v, vm, 1e-2, 0.9, 0.999, 1e-8, step)
+    assert (p.cpu() - ref.detach()).abs().max() <= 1e-6

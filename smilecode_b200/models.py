@@ -120,6 +120,22 @@ class Encoder(nn.Module):
             cin, cout = (2 ** lvl) * c, (2 ** (lvl + 1)) * c
             setattr(self, f"conv{lvl}", nn.Sequential(nn.AvgPool3d(2), ConvInsBlock(cin, cout), ConvInsBlock(cout, cout)))
 
+    def forward_train(self, x):
+        """Same graph through the autograd Functions (every forward and backward step is one of our kernels)."""
+        from . import autograd as ag
+        outs: List[torch.Tensor] = []
+        c0 = self.conv0[0].main
+        t = ag.ConvLReLU.apply(x, c0.weight, c0.bias)
+        for lvl in range(5):
+            seq = getattr(self, f"conv{lvl}")
+            a = ag.ConvINLReLU.apply(t, seq[1].main.weight, seq[1].main.bias, False)
+            if lvl < 4:
+                out, t = ag.ConvINLReLU.apply(a, seq[2].main.weight, seq[2].main.bias, True)
+            else:
+                out = ag.ConvINLReLU.apply(a, seq[2].main.weight, seq[2].main.bias, False)
+            outs.append(out)
+        return tuple(outs)
+
     def forward(self, x):
         outs: List[torch.Tensor] = []
         t = self.conv0[0](x)
@@ -163,6 +179,14 @@ class CWM(nn.Module):
                                   nn.Conv3d(channels, self.num_fields, 3, 1, 1), nn.Softmax(dim=1))
         self.upsample = nn.Upsample(scale_factor=2, mode="trilinear", align_corners=True)
 
+    def forward_train(self, x):
+        from . import autograd as ag
+        u = ag.Upsample2x.apply(x, 1.0)
+        a = ag.ConvINLReLU.apply(u, self.conv[0].main.weight, self.conv[0].main.bias, False)
+        a = ag.ConvINLReLU.apply(a, self.conv[1].main.weight, self.conv[1].main.bias, False)
+        logits = ag.Conv.apply(a, self.conv[2].weight, self.conv[2].bias)
+        return ag.CwmFuse.apply(u, logits)
+
     def forward(self, x):
         u = ops.upsample2x(x)
         raw, st = self.conv[0].raw(u)
@@ -199,7 +223,38 @@ class ModeT(nn.Module):
         pb, mdt = getattr(self, f"projblock{level}"), getattr(self, f"mdt{level}")
         return mdt(pb(feat_f), pb.of_warped(feat_m, flow))
 
+    def _forward_train(self, moving, fixed):
+        """Training graph (models.py:377-412) through smilecode_b200.autograd: unfused ops so that every node has a
+        hand-written backward kernel; the tensor glue (cat / slicing / add / scalar multiply) is torch's."""
+        from . import autograd as ag
+        B = moving.shape[0]
+        feats = self.encoder.forward_train(torch.cat([moving, fixed], 0))
+        M = [f[:B] for f in feats]
+        Fx = [f[B:] for f in feats]
+
+        def proj(level, feat):
+            pb = getattr(self, f"projblock{level}")
+            return ag.ProjLN.apply(feat, pb.proj.weight, pb.proj.bias, pb.norm.weight, pb.norm.bias, pb.norm.eps)
+
+        def attend(level, feat_f, feat_m):
+            mdt = getattr(self, f"mdt{level}")
+            return ag.Attention.apply(proj(level, feat_f), proj(level, feat_m), mdt.rpb if mdt.use_rpb else None,
+                                      mdt.num_heads, mdt.scale)
+
+        flow = self.cwm5.forward_train(attend(5, Fx[4], M[4]))
+        w = self.cwm4.forward_train(attend(4, Fx[3], ag.Warp.apply(M[3], flow)))
+        flow = ag.Warp.apply(ag.Upsample2x.apply(flow, 2.0), w) + w
+        w = self.cwm3.forward_train(attend(3, Fx[2], ag.Warp.apply(M[2], flow)))
+        flow = ag.Warp.apply(ag.Upsample2x.apply(flow, 2.0), w) + w
+        w = attend(2, Fx[1], ag.Warp.apply(M[1], flow))
+        flow = ag.Upsample2x.apply(ag.Warp.apply(flow, w) + w, 2.0)
+        w = attend(1, Fx[0], ag.Warp.apply(M[0], flow))
+        flow = ag.Warp.apply(flow, w) + w
+        return ag.Warp.apply(moving, flow), flow
+
     def forward(self, moving, fixed):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._forward_train(moving, fixed)
         B = moving.shape[0]
         feats = self.encoder(torch.cat([moving, fixed], 0))     # shared weights: one batched pass
         M = [f[:B] for f in feats]

@@ -177,3 +177,64 @@ def test_adam_amsgrad_matches_torch():
         opt.step()
         ops.adam_amsgrad_step(p, dev(grad), m, v, vm, 1e-2, 0.9, 0.999, 1e-8, step)
     assert (p.cpu() - ref.detach()).abs().max() <= 1e-6
+
+
+def test_end_to_end_training_gradients_match_reference_autograd():
+    """One training step's gradients (NCC + Grad3d loss, train.py:126-132) for every parameter vs autograd of the
+    CPU oracle of the whole model."""
+    from smilecode_b200 import losses, models
+    from smilecode_b200.synth import make_pair
+    shape, heads = (16, 32, 32), [8, 4, 2, 1, 1]
+    sd = orc.synth_state_dict(seed=1234, num_heads=heads)
+    moving, fixed = make_pair(shape, batch=1, seed=24)
+    # reference gradients on the CPU
+    sd_r = {k: v.clone().requires_grad_(v.dtype.is_floating_point and not k.endswith("grid")) for k, v in sd.items()}
+    y, flow = orc.modet_forward(moving, fixed, sd_r, num_heads=heads, scale=1.0, library_ops=True)
+    loss_r = orc.ncc_vxm(y, fixed) + orc.grad3d_l2(flow)
+    loss_r.backward()
+    # ours
+    model = models.ModeT(shape, head_dim=6, num_heads=heads, scale=1)
+    model.load_state_dict(sd, strict=False)
+    model = model.cuda().train()
+    y_d, flow_d = model(moving.cuda(), fixed.cuda())
+    loss = losses.NCC_vxm()(y_d, fixed.cuda()) + losses.Grad3d(penalty="l2")(flow_d, fixed.cuda())
+    loss.backward()
+    assert abs(float(loss.detach()) - float(loss_r.detach())) <= 1e-4 * max(1.0, abs(float(loss_r)))
+    worst = {}
+    for name, p in model.named_parameters():
+        gr = sd_r[name].grad
+        assert gr is not None and p.grad is not None, name
+        worst[name] = float((p.grad.cpu() - gr).abs().max() / gr.abs().max().clamp_min(1e-12))
+    # a bias in front of an InstanceNorm has exactly zero gradient (the norm removes the mean): only noise there
+    live = {k: v for k, v in worst.items() if not (k.endswith("main.bias") and ".conv.2." not in k and "conv0.0" not in k)}
+    print("worst relative gradient errors:", sorted(live.items(), key=lambda kv: -kv[1])[:5])
+    bad = {k: v for k, v in live.items() if v > 1e-3}
+    assert not bad, bad
+
+
+def test_trainer_steps_reduce_the_loss_and_match_torch_adam():
+    from smilecode_b200 import models
+    from smilecode_b200.synth import make_pair, randomize_weights
+    from smilecode_b200.train import Trainer
+    shape, heads = (16, 32, 32), [8, 4, 2, 1, 1]
+    model = models.ModeT(shape, head_dim=6, num_heads=heads, scale=1)
+    randomize_weights(model, seed=3)
+    model = model.cuda()
+    moving, fixed = (t.cuda() for t in make_pair(shape, batch=1, seed=9))
+    # twin updated by torch.optim.Adam from the same gradients (first step)
+    import copy
+    twin = copy.deepcopy(model)
+    tr = Trainer(model, lr=1e-3)
+    losses_seen = []
+    for it in range(6):
+        if it == 0:
+            opt = torch.optim.Adam(twin.parameters(), lr=1e-3, amsgrad=True)
+        loss, _, _ = tr.step(moving, fixed)
+        losses_seen.append(float(loss))
+        if it == 0:
+            for p, q in zip(model.parameters(), twin.parameters()):
+                q.grad = p.grad.clone()
+            opt.step()
+            for (n, p), q in zip(model.named_parameters(), twin.parameters()):
+                assert (p.data - q.data).abs().max() <= 1e-6, n
+    assert losses_seen[-1] < losses_seen[0], losses_seen

@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--breakdown", action="store_true", help="print a per-kernel CUDA-event breakdown to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -274,6 +275,34 @@ def main():
                     print(f"  {ms:9.3f} ms  {100 * ms / tot:5.1f}%  x{calls:<3d} {name}", file=sys.stderr)
                 print(f"  total of kernels {tot:.3f} ms", file=sys.stderr)
 
+    # ---------------- training step: fp32, one pair per GPU, NCC + Grad3d loss, hand-written
+    # backward kernels, one flat-bucket NCCL all-reduce of the gradients when N > 1, fused Adam(amsgrad) update
+    train = None
+    if not args.no_train:
+        from smilecode_b200.train import Trainer
+        tmodel = models.ModeT(SHAPE, head_dim=6, num_heads=HEADS, scale=1)
+        randomize_weights(tmodel, seed=1234)
+        tmodel = tmodel.to(dev)
+        trainer = Trainer(tmodel, lr=1e-4, distributed=world > 1)
+        for _ in range(2):
+            trainer.step(moving, fixed)
+        barrier()
+        l0 = _lib.LAUNCHES
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        TK = min(K, 5)
+        t0.record(stream)
+        for _ in range(TK):
+            tloss, _, _ = trainer.step(moving, fixed)
+        t1.record(stream)
+        barrier()
+        tms = reduce_max(t0.elapsed_time(t1)) / TK
+        train = {"value": world * 1e3 / tms, "unit": "pairs/s", "ms_per_step": tms, "steps": TK,
+                 "gpu_launches_per_step": (_lib.LAUNCHES - l0) // TK, "loss": float(tloss),
+                 "config": "fp32 training step, 1 pair per GPU, NCC_vxm(9) + Grad3d(l2), Adam(amsgrad); "
+                           + ("flat-bucket NCCL gradient all-reduce" if world > 1 else "single GPU, no collective")}
+        del trainer, tmodel
+        torch.cuda.empty_cache()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
@@ -303,7 +332,7 @@ def main():
                 "dtype": "f32", "data": "synthetic", "config": workload_config(1, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / K},
-                "gpu_launches": launches, "gpu_launches_per_step": launches // K, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": launches, "gpu_launches_per_step": launches // K, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "train": train}
         if breakdown:
             line["kernel_ms"] = {name: round(ms, 4) for ms, _, name in breakdown[:12]}
         print(json.dumps(line))

@@ -53,5 +53,14 @@ if rank == 0:
     print(f"train step {shape} fp32 B=1/GPU x{world}: {ms:.2f} ms/step -> {world * 1e3 / ms:.2f} pairs/s; "
           f"loss {float(loss):.5f} ncc {float(ncc):.5f} reg {float(reg):.5f}; launches/step {(_lib.LAUNCHES - l0) // steps}; "
           f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
+if os.environ.get("PROFILE") and rank == 0:
+    _lib.profile_start()
+    tr.step(moving, fixed)
+    prof = _lib.profile_stop()
+    rows = sorted(((v[1], v[0], k) for k, v in prof.items()), reverse=True)
+    tot = sum(r[0] for r in rows)
+    for ms_, calls, name in rows[:40]:
+        print(f"  {ms_:9.3f} ms  {100 * ms_ / tot:5.1f}%  x{calls:<3d} {name}")
+    print(f"  total of kernels {tot:.3f} ms")
 if world > 1:
     dist.destroy_process_group()

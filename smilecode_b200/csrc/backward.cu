@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const float* __restric
   const float* gb = g + (long long)b * 3 * heads * N;
   float* dqb = dq + (long long)b * N * Cc;
   float* dlb = dl_out + (long long)b * N * heads * 27;
+  const bool even = (hd % 2 == 0);  // rows are 8-byte aligned: float2 loads
   float racc[27];  // this thread's share of d_rpb[head, :]
 #pragma unroll
   for (int t = 0; t < 27; ++t) racc[t] = 0.f;
@@ -176,7 +177,14 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const float* __restric
       float acc = 0.f;
       if (dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W) {
         const float* kr = kb + (((long long)dd * H + hh) * W + ww) * Cc + head * hd;
-        for (int c = 0; c < hd; ++c) acc = fmaf(__ldg(qr + c), __ldg(kr + c), acc);
+        if (even) {
+          for (int c = 0; c < hd; c += 2) {
+            const float2 qv = __ldg(reinterpret_cast<const float2*>(qr + c)), kv = __ldg(reinterpret_cast<const float2*>(kr + c));
+            acc = fmaf(qv.x, kv.x, fmaf(qv.y, kv.y, acc));
+          }
+        } else {
+          for (int c = 0; c < hd; ++c) acc = fmaf(__ldg(qr + c), __ldg(kr + c), acc);
+        }
       }
       lg[t] = acc * scale + (rpb ? __ldg(rpb + head * 27 + t) : 0.f);
       m = fmaxf(m, lg[t]);
@@ -197,23 +205,39 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const float* __restric
       const float gv = g0 * (float)(t / 9 - 1) + g1 * (float)((t / 3) % 3 - 1) + g2 * (float)(t % 3 - 1);
       dot = fmaf(lg[t], gv, dot);
     }
-    float* dlr = dlb + (p * heads + head) * 27;
+    float* dlr = dlb + (long long)head * 27 * N + p;   // [heads][27][N]: coalesced here and in the dk gather
 #pragma unroll
     for (int t = 0; t < 27; ++t) {
       const float gv = g0 * (float)(t / 9 - 1) + g1 * (float)((t / 3) % 3 - 1) + g2 * (float)(t % 3 - 1);
       lg[t] = lg[t] * (gv - dot);  // d_logit
-      dlr[t] = lg[t];
+      dlr[(long long)t * N] = lg[t];
       racc[t] += lg[t];
     }
-    for (int c = 0; c < hd; ++c) {
-      float acc = 0.f;
+    if (even) {
+      for (int c = 0; c < hd; c += 2) {
+        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-      for (int t = 0; t < 27; ++t) {
-        const int dd = d + t / 9 - 1, hh = h + (t / 3) % 3 - 1, ww = w + t % 3 - 1;
-        if (dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W)
-          acc = fmaf(lg[t], __ldg(kb + (((long long)dd * H + hh) * W + ww) * Cc + head * hd + c), acc);
+        for (int t = 0; t < 27; ++t) {
+          const int dd = d + t / 9 - 1, hh = h + (t / 3) % 3 - 1, ww = w + t % 3 - 1;
+          if (dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W) {
+            const float2 kv = __ldg(reinterpret_cast<const float2*>(kb + (((long long)dd * H + hh) * W + ww) * Cc + head * hd + c));
+            a0 = fmaf(lg[t], kv.x, a0);
+            a1 = fmaf(lg[t], kv.y, a1);
+          }
+        }
+        *reinterpret_cast<float2*>(dqb + p * Cc + head * hd + c) = make_float2(a0 * scale, a1 * scale);
       }
-      dqb[p * Cc + head * hd + c] = acc * scale;
+    } else {
+      for (int c = 0; c < hd; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < 27; ++t) {
+          const int dd = d + t / 9 - 1, hh = h + (t / 3) % 3 - 1, ww = w + t % 3 - 1;
+          if (dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W)
+            acc = fmaf(lg[t], __ldg(kb + (((long long)dd * H + hh) * W + ww) * Cc + head * hd + c), acc);
+        }
+        dqb[p * Cc + head * hd + c] = acc * scale;
+      }
     }
   }
   if (drpb != nullptr) {
@@ -253,9 +277,17 @@ __global__ void __launch_bounds__(128) attn_bwd_dk_kernel(const float* __restric
       const int dd = d - (t / 9 - 1), hh = h - ((t / 3) % 3 - 1), ww = w - (t % 3 - 1);
       if (dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W) {
         const long long n = ((long long)dd * H + hh) * W + ww;
-        const float gv = __ldg(dlb + (n * heads + head) * 27 + t);
+        const float gv = __ldg(dlb + ((long long)head * 27 + t) * N + n);
         const float* qr = qb + n * Cc + head * hd;
-        for (int c = 0; c < hd; ++c) acc[c] = fmaf(gv, __ldg(qr + c), acc[c]);
+        if (hd % 2 == 0) {
+          for (int c = 0; c < hd; c += 2) {
+            const float2 qv = __ldg(reinterpret_cast<const float2*>(qr + c));
+            acc[c] = fmaf(gv, qv.x, acc[c]);
+            acc[c + 1] = fmaf(gv, qv.y, acc[c + 1]);
+          }
+        } else {
+          for (int c = 0; c < hd; ++c) acc[c] = fmaf(gv, __ldg(qr + c), acc[c]);
+        }
       }
     }
     for (int c = 0; c < hd; ++c) dkb[p * Cc + head * hd + c] = acc[c] * scale;
@@ -265,6 +297,11 @@ __global__ void __launch_bounds__(128) attn_bwd_dk_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------
 // ProjectionLayer backward.  z = W x + b; y = gamma * (z - mean) * rstd + beta.
 // ------------------------------------------------------------------------------------------------
+// Phase A (thread = voxel of a 128-voxel tile): recompute z and the LayerNorm statistics, form dz and the
+// per-voxel contributions to d_gamma / d_beta, park them (and the x tile) in shared memory, write d_feat.
+// Phase B (thread = output element): every parameter-gradient element sums its 128 products from shared
+// memory into a register that lives across the CTA's grid-stride loop; one atomicAdd per element and CTA at
+// the end.  No warp shuffles, no per-voxel atomics.
 template <int C>
 __global__ void __launch_bounds__(128) proj_ln_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ feat,
                                                           const float* __restrict__ weight, const float* __restrict__ bias,
@@ -272,39 +309,45 @@ __global__ void __launch_bounds__(128) proj_ln_bwd_kernel(const float* __restric
                                                           float* __restrict__ dweight, float* __restrict__ dbias,
                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int Cin,
                                                           long long N, float eps) {
+  constexpr int TV = 128, XP = TV + 1;
   extern __shared__ float smem[];
-  float* s_w = smem;                  // [Cin][C]
-  float* s_b = s_w + Cin * C;         // bias, gamma
-  float* s_dw = s_b + 2 * C;          // [Cin][C] CTA partial of d_weight
-  float* s_dv = s_dw + Cin * C;       // d_bias, d_gamma, d_beta partials [3][C]
+  float* s_w = smem;                   // [Cin][C]
+  float* s_b = s_w + Cin * C;          // bias, gamma
+  float* s_dz = s_b + 2 * C;           // [TV][C]
+  float* s_gx = s_dz + TV * C;         // [TV][C]  gy * xhat
+  float* s_gy = s_gx + TV * C;         // [TV][C]  gy
+  float* s_x = s_gy + TV * C;          // [Cin][XP]
   for (int i = threadIdx.x; i < Cin * C; i += blockDim.x) {
     const int ci = i / C, c = i - ci * C;
     s_w[i] = weight[c * Cin + ci];
-    s_dw[i] = 0.f;
   }
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     s_b[i] = bias[i];
     s_b[C + i] = gamma[i];
-    s_dv[i] = s_dv[C + i] = s_dv[2 * C + i] = 0.f;
   }
   __syncthreads();
   const int b = blockIdx.y;
   const float* fb = feat + (long long)b * Cin * N;
   const float* gb = gout + (long long)b * N * C;
   float* dfb = dfeat ? dfeat + (long long)b * Cin * N : nullptr;
-  const int lane = threadIdx.x & 31;
-  for (long long p0 = (long long)blockIdx.x * blockDim.x; p0 < N; p0 += (long long)gridDim.x * blockDim.x) {
+  const int nout = Cin * C;
+  constexpr int MAXO = 48;             // outputs per thread: Cin*C <= 128*48 (128 x 48 at the coarsest level)
+  float wacc[MAXO];
+#pragma unroll
+  for (int i = 0; i < MAXO; ++i) wacc[i] = 0.f;
+  float vacc[3] = {0.f, 0.f, 0.f};     // d_bias / d_gamma / d_beta element of thread c < C
+  for (long long p0 = (long long)blockIdx.x * TV; p0 < N; p0 += (long long)gridDim.x * TV) {
     const long long p = p0 + threadIdx.x;
     const bool ok = p < N;
     float z[C], dz[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) z[c] = s_b[c];
-    if (ok)
-      for (int ci = 0; ci < Cin; ++ci) {
-        const float x = __ldg(fb + (long long)ci * N + p);
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float x = ok ? __ldg(fb + (long long)ci * N + p) : 0.f;
+      s_x[ci * XP + threadIdx.x] = x;
 #pragma unroll
-        for (int c = 0; c < C; ++c) z[c] = fmaf(x, s_w[ci * C + c], z[c]);
-      }
+      for (int c = 0; c < C; ++c) z[c] = fmaf(x, s_w[ci * C + c], z[c]);
+    }
     float mean = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) mean += z[c];
@@ -318,12 +361,8 @@ __global__ void __launch_bounds__(128) proj_ln_bwd_kernel(const float* __restric
     for (int c = 0; c < C; ++c) {
       const float gy = ok ? __ldg(gb + p * C + c) : 0.f;
       const float xh = (z[c] - mean) * rstd;
-      // parameter gradients of the LayerNorm: warp-reduce, one shared atomic per warp
-      const float dgam = warp_sum(gy * xh), dbet = warp_sum(gy);
-      if (lane == 0) {
-        atomicAdd(&s_dv[C + c], dgam);
-        atomicAdd(&s_dv[2 * C + c], dbet);
-      }
+      s_gx[threadIdx.x * C + c] = gy * xh;
+      s_gy[threadIdx.x * C + c] = gy;
       const float dxh = gy * s_b[C + c];
       dz[c] = dxh;
       z[c] = xh;
@@ -334,31 +373,67 @@ __global__ void __launch_bounds__(128) proj_ln_bwd_kernel(const float* __restric
     s2 *= (1.0f / C);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      dz[c] = rstd * (dz[c] - s1 - z[c] * s2);
-      const float dbv = warp_sum(dz[c]);
-      if (lane == 0) atomicAdd(&s_dv[c], dbv);
+      dz[c] = ok ? rstd * (dz[c] - s1 - z[c] * s2) : 0.f;
+      s_dz[threadIdx.x * C + c] = dz[c];
     }
-    for (int ci = 0; ci < Cin; ++ci) {
-      const float x = ok ? __ldg(fb + (long long)ci * N + p) : 0.f;
-      float dxv = 0.f;
+    if (ok && dfb != nullptr)
+      for (int ci = 0; ci < Cin; ++ci) {
+        float dxv = 0.f;
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        dxv = fmaf(dz[c], s_w[ci * C + c], dxv);
-        const float dwv = warp_sum(dz[c] * x);
-        if (lane == 0) atomicAdd(&s_dw[ci * C + c], dwv);
+        for (int c = 0; c < C; ++c) dxv = fmaf(dz[c], s_w[ci * C + c], dxv);
+        dfb[(long long)ci * N + p] = dxv;
       }
-      if (ok && dfb != nullptr) dfb[(long long)ci * N + p] = dxv;
+    __syncthreads();
+    // phase B (when Cin*C < 128 the 128 voxels are split over 128 / (Cin*C) thread groups)
+    if (nout >= 128) {
+#pragma unroll
+      for (int i = 0; i < MAXO; ++i) {
+        const int o = threadIdx.x + i * 128;
+        if (o < nout) {
+          const int ci = o / C, c = o - ci * C;
+          float a = wacc[i];
+          for (int v = 0; v < TV; ++v) a = fmaf(s_dz[v * C + c], s_x[ci * XP + v], a);
+          wacc[i] = a;
+        }
+      }
+    } else {
+      const int ngroups = 128 / nout;
+      const int o = threadIdx.x % nout, grp = threadIdx.x / nout;
+      if (grp < ngroups) {
+        const int ci = o / C, c = o - ci * C;
+        float a = wacc[0];
+        for (int v = grp; v < TV; v += ngroups) a = fmaf(s_dz[v * C + c], s_x[ci * XP + v], a);
+        wacc[0] = a;
+      }
     }
+    if (threadIdx.x < C) {
+      const int c = threadIdx.x;
+      for (int v = 0; v < TV; ++v) {
+        vacc[0] += s_dz[v * C + c];
+        vacc[1] += s_gx[v * C + c];
+        vacc[2] += s_gy[v * C + c];
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < Cin * C; i += blockDim.x) {
-    const int ci = i / C, c = i - ci * C;
-    atomicAdd(dweight + c * Cin + ci, s_dw[i]);
+  if (nout >= 128) {
+#pragma unroll
+    for (int i = 0; i < MAXO; ++i) {
+      const int o = threadIdx.x + i * 128;
+      if (o < nout) {
+        const int ci = o / C, c = o - ci * C;
+        atomicAdd(dweight + c * Cin + ci, wacc[i]);
+      }
+    }
+  } else if ((int)threadIdx.x / nout < 128 / nout) {
+    const int o = threadIdx.x % nout;
+    const int ci = o / C, c = o - ci * C;
+    atomicAdd(dweight + c * Cin + ci, wacc[0]);
   }
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    atomicAdd(dbias + i, s_dv[i]);
-    atomicAdd(dgamma + i, s_dv[C + i]);
-    atomicAdd(dbeta + i, s_dv[2 * C + i]);
+  if (threadIdx.x < C) {
+    atomicAdd(dbias + threadIdx.x, vacc[0]);
+    atomicAdd(dgamma + threadIdx.x, vacc[1]);
+    atomicAdd(dbeta + threadIdx.x, vacc[2]);
   }
 }
 
@@ -455,7 +530,11 @@ template <int C>
 static int launch_pl_bwd(const float* gout, const float* feat, const float* weight, const float* bias, const float* gamma,
                          float* dfeat, float* dweight, float* dbias, float* dgamma, float* dbeta, int B, int Cin, long long N,
                          float eps, cudaStream_t st) {
-  const size_t smem = (size_t)(2 * Cin * C + 5 * C) * sizeof(float);
+  if ((long long)Cin * C > 128LL * 48) {
+    set_error("proj_ln_bwd: Cin*C = %d exceeds the compiled limit %d", Cin * C, 128 * 48);
+    return SMILE_ERR_UNSUPPORTED;
+  }
+  const size_t smem = (size_t)(Cin * C + 2 * C + 3 * 128 * C + Cin * 129) * sizeof(float);
   auto kern = proj_ln_bwd_kernel<C>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -128,20 +128,24 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __rest
     }
   }
 
-  // weights of one K-chunk: global [co][ci][27] -> shared [ci][27][co]
+  // weights of one K-chunk: global [co][ci][27] -> shared [ci][27][co], as fire-and-forget 4-byte cp.async
+  // copies (zero-filled outside the tensor) so the global-load latency overlaps the multiply phase
   auto stage_weights = [&](int chunk, int buf) {
-    float* sw = reinterpret_cast<float*>(smem + C::OFF_W + buf * C::W_STRIDE);
+    const uint32_t sw = smem_u32(smem + C::OFF_W + buf * C::W_STRIDE);
     const int ci0 = chunk * CIC;
     for (int e = tid; e < C::W_ELEMS; e += C::THREADS) {
       const int co = e / (CIC * 27);
       const int rem = e - co * (CIC * 27);  // ci_local * 27 + tap: contiguous in global memory
       const int ci = ci0 + rem / 27;
-      float v = 0.f;
-      if (ci < Cin && co0 + co < Cout) v = __ldg(weight + ((long long)(co0 + co) * Cin + ci0) * 27 + rem);
-      sw[rem * CO + co] = v;
+      const bool ok = ci < Cin && co0 + co < Cout;
+      const float* src = weight + (ok ? ((long long)(co0 + co) * Cin + ci0) * 27 + rem : 0);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sw + 4 * (rem * CO + co)), "l"(src),
+                   "r"(ok ? 4 : 0)
+                   : "memory");
     }
   };
   stage_weights(0, 0);
+  asm volatile("cp.async.wait_all;" ::: "memory");
 
   float2 acc[V][CO / 2];
 #pragma unroll
@@ -245,6 +249,7 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __rest
         }
       }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");  // next chunk's weights have landed (issued before the math)
     __syncthreads();  // everyone is done with buffer `buf` before it is refilled two chunks later
   }
 

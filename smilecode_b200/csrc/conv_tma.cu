@@ -96,7 +96,10 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __rest
   float* s_mr = reinterpret_cast<float*>(smem + C::OFF_MR);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tx = lane % TWL, ty = warp * LH + lane / TWL;
+  // 16-wide tiles put two rows in a warp; rows 2 apart (pitch 24 floats -> 48 = 16 mod 32 banks) keep the
+  // two half-warps on disjoint shared-memory banks, adjacent rows would 2-way conflict
+  const int tx = lane % TWL;
+  const int ty = (LH == 2) ? ((warp >> 1) * 4 + (warp & 1) + 2 * (lane / TWL)) : (warp * LH + lane / TWL);
   int t = blockIdx.x;
   const int tw_i = t % tiles_w;
   t /= tiles_w;

@@ -19,6 +19,14 @@ inline int grid_for(long long n, int block, int per_sm = 16) {
   const long long cap = (long long)kNumSMs * per_sm;
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -37,60 +45,102 @@ __global__ void flip_weights_kernel(const float* __restrict__ w, float* __restri
 }
 
 // d_weight[co][ci][t] += sum_{b,v} dy[b,co,v] * x[b,ci,v + off(t)];  d_bias[co] += sum dy (ci == 0 CTAs)
+//
+// CTA = 4 warps = 4 rows x 32 columns of the (H, W) plane, marching a depth chunk; blockIdx.y = (group of 4
+// output channels, input channel).  The input neighbourhood comes from a 4-plane shared-memory ring of
+// (4+2) x (32+2) halo tiles, zero filled outside the volume, so the 27 taps are immediate-offset LDS with no
+// bounds logic; the 4 x 27 accumulators of a thread are packed channel pairs (fma.rn.f32x2).
 constexpr int WG_CO = 4;
+constexpr int WG_PW = 36;            // ring row pitch (34 used)
+constexpr int WG_PLANE = 6 * WG_PW;  // floats per ring plane
 __global__ void __launch_bounds__(128) conv3d_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                            float* __restrict__ dw, float* __restrict__ db, int B, int Cin,
                                                            int Cout, int D, int H, int W, int dchunk, int tiles_h,
                                                            int tiles_w) {
-  // CTA: 4 warps = 4 rows x 32 columns of the (H, W) plane, marching `dchunk` depths; blockIdx.y = (co group, ci)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ float s_x[4][WG_PLANE];
+  __shared__ float s_part[4][WG_CO * 27 + WG_CO];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int t = blockIdx.x;
   const int tw = t % tiles_w;
   t /= tiles_w;
   const int th = t % tiles_h;
   t /= tiles_h;
-  const int dc = t;  // depth chunk index (batch folded in by blockIdx.z)
+  const int dc = t;
   const int b = blockIdx.z;
   const int cog = blockIdx.y / Cin, ci = blockIdx.y % Cin;
   const int co0 = cog * WG_CO;
-  const int h = th * 4 + warp, w = tw * 32 + lane;
+  const int h0 = th * 4, w0 = tw * 32;
+  const int h = h0 + warp, w = w0 + lane;
   const int HW = H * W;
   const long long N = (long long)D * HW;
   const bool inside = (h < H) && (w < W);
   const float* xb = x + ((long long)b * Cin + ci) * N;
   const float* dyb = dy + ((long long)b * Cout + co0) * N;
-  float acc[WG_CO][27];
+  float2 acc[WG_CO / 2][27];
   float bsum[WG_CO];
 #pragma unroll
-  for (int c = 0; c < WG_CO; ++c) {
-    bsum[c] = 0.f;
+  for (int c = 0; c < WG_CO; ++c) bsum[c] = 0.f;
 #pragma unroll
-    for (int k = 0; k < 27; ++k) acc[c][k] = 0.f;
-  }
+  for (int c = 0; c < WG_CO / 2; ++c)
+#pragma unroll
+    for (int k = 0; k < 27; ++k) acc[c][k] = make_float2(0.f, 0.f);
   const int d_begin = dc * dchunk, d_end = min(D, d_begin + dchunk);
-  if (inside) {
-    for (int d = d_begin; d < d_end; ++d) {
-      float g[WG_CO];
+
+  // cooperative load of one halo plane (6 x 34 = 204 values, <= 2 per thread) into ring slot (dd & 3):
+  // global loads are issued early into registers (fetch) and parked in shared memory after the math (commit)
+  const int e0 = tid, e1 = tid + 128;
+  const int r0 = e0 / 34, c0 = e0 - r0 * 34, r1 = e1 / 34, c1 = e1 - r1 * 34;
+  const bool ok0 = (h0 - 1 + r0 >= 0) && (h0 - 1 + r0 < H) && (w0 - 1 + c0 >= 0) && (w0 - 1 + c0 < W);
+  const bool ok1 = (e1 < 204) && (h0 - 1 + r1 >= 0) && (h0 - 1 + r1 < H) && (w0 - 1 + c1 >= 0) && (w0 - 1 + c1 < W);
+  const long long o0 = (long long)(h0 - 1 + r0) * W + (w0 - 1 + c0), o1 = (long long)(h0 - 1 + r1) * W + (w0 - 1 + c1);
+  const int s0 = r0 * WG_PW + c0, s1 = r1 * WG_PW + c1;
+  float pre0 = 0.f, pre1 = 0.f;
+  auto fetch = [&](int dd) {
+    const bool okd = dd >= 0 && dd < D;
+    pre0 = (okd && ok0) ? __ldg(xb + (long long)dd * HW + o0) : 0.f;
+    pre1 = (okd && ok1) ? __ldg(xb + (long long)dd * HW + o1) : 0.f;
+  };
+  auto commit = [&](int dd) {
+    float* dst = s_x[dd & 3];
+    dst[s0] = pre0;
+    if (e1 < 204) dst[s1] = pre1;
+  };
+  fetch(d_begin - 1);
+  commit(d_begin - 1);
+  fetch(d_begin);
+  commit(d_begin);
+  fetch(d_begin + 1);
+  commit(d_begin + 1);
+  __syncthreads();
+  const int toff = warp * WG_PW + lane;  // tile position of tap (kh=0, kw=0)
+  for (int d = d_begin; d < d_end; ++d) {
+    fetch(d + 2);  // lands in slot (d+2)&3 == (d-2)&3, which nobody reads in this iteration
+    float g[WG_CO];
 #pragma unroll
-      for (int c = 0; c < WG_CO; ++c) g[c] = (co0 + c < Cout) ? __ldg(dyb + (long long)c * N + (long long)d * HW + h * W + w) : 0.f;
+    for (int c = 0; c < WG_CO; ++c)
+      g[c] = (inside && co0 + c < Cout) ? __ldg(dyb + (long long)c * N + (long long)d * HW + h * W + w) : 0.f;
 #pragma unroll
-      for (int c = 0; c < WG_CO; ++c) bsum[c] += g[c];
+    for (int c = 0; c < WG_CO; ++c) bsum[c] += g[c];
 #pragma unroll
-      for (int k = 0; k < 27; ++k) {
-        const int dd = d + k / 9 - 1, hh = h + (k / 3) % 3 - 1, ww = w + k % 3 - 1;
-        float xv = 0.f;
-        if (dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W) xv = __ldg(xb + (long long)dd * HW + hh * W + ww);
+    for (int kd = 0; kd < 3; ++kd) {
+      const float* pl = s_x[(d - 1 + kd) & 3] + toff;
 #pragma unroll
-        for (int c = 0; c < WG_CO; ++c) acc[c][k] = fmaf(g[c], xv, acc[c][k]);
+      for (int j = 0; j < 9; ++j) {
+        const float xv = pl[(j / 3) * WG_PW + (j % 3)];
+        const float2 xb2 = make_float2(xv, xv);
+#pragma unroll
+        for (int c = 0; c < WG_CO / 2; ++c)
+          acc[c][kd * 9 + j] = fma2(xb2, make_float2(g[2 * c], g[2 * c + 1]), acc[c][kd * 9 + j]);
       }
     }
+    commit(d + 2);
+    __syncthreads();
   }
-  __shared__ float s_part[4][WG_CO * 27 + WG_CO];
 #pragma unroll
   for (int c = 0; c < WG_CO; ++c) {
 #pragma unroll
     for (int k = 0; k < 27; ++k) {
-      const float v = warp_sum(acc[c][k]);
+      const float v = warp_sum((c & 1) ? acc[c / 2][k].y : acc[c / 2][k].x);
       if (lane == 0) s_part[warp][c * 27 + k] = v;
     }
     const float v = warp_sum(bsum[c]);

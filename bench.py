@@ -258,8 +258,16 @@ def main():
         k_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
         peak, peak_src = measured_peaks()
         achieved = FUSED_L1_BYTES_PER_VOXEL * N1 / (k_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
+            with open(os.path.join(ROOT, "profiles", "fused_l1_traffic.json")) as f:
+                tj = json.load(f)
+            traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj["source"]
+        except Exception:
+            pass
         roofline = {"kernel": "modet_fused_fwd (L1: attention heads=1 + flow compose + warp moving)", "bound": "hbm",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_source": traffic_src,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": FUSED_L1_BYTES_PER_VOXEL * N1,
                     "launch_ms": k_ms}
 

@@ -113,12 +113,17 @@ __global__ void __launch_bounds__(128) conv3d_wgrad_kernel(const float* __restri
   commit(d_begin + 1);
   __syncthreads();
   const int toff = warp * WG_PW + lane;  // tile position of tap (kh=0, kw=0)
-  for (int d = d_begin; d < d_end; ++d) {
-    fetch(d + 2);  // lands in slot (d+2)&3 == (d-2)&3, which nobody reads in this iteration
-    float g[WG_CO];
+  // the output gradients are streamed from DRAM exactly once: fetch them one depth ahead as well
+  float g[WG_CO], gn[WG_CO];
+  auto fetch_g = [&](int dd, float (&dst)[WG_CO]) {
 #pragma unroll
     for (int c = 0; c < WG_CO; ++c)
-      g[c] = (inside && co0 + c < Cout) ? __ldg(dyb + (long long)c * N + (long long)d * HW + h * W + w) : 0.f;
+      dst[c] = (inside && dd < d_end && co0 + c < Cout) ? __ldg(dyb + (long long)c * N + (long long)dd * HW + h * W + w) : 0.f;
+  };
+  fetch_g(d_begin, g);
+  for (int d = d_begin; d < d_end; ++d) {
+    fetch(d + 2);  // lands in slot (d+2)&3 == (d-2)&3, which nobody reads in this iteration
+    fetch_g(d + 1, gn);
 #pragma unroll
     for (int c = 0; c < WG_CO; ++c) bsum[c] += g[c];
 #pragma unroll
@@ -134,6 +139,8 @@ __global__ void __launch_bounds__(128) conv3d_wgrad_kernel(const float* __restri
       }
     }
     commit(d + 2);
+#pragma unroll
+    for (int c = 0; c < WG_CO; ++c) g[c] = gn[c];
     __syncthreads();
   }
 #pragma unroll

@@ -361,10 +361,18 @@ int launch_conv3d_flip_weights(const float* w, float* wT, int Cout, int Cin, cud
   return check_launch("conv3d_flip_weights");
 }
 
+int launch_conv3d_wgrad_tma(const float* x, const float* dy, float* dw, float* db, int B, int Cin, int Cout, int D, int H,
+                            int W, cudaStream_t st, bool* handled);
+
 int launch_conv3d_wgrad(const float* x, const float* dy, float* dw, float* db, int B, int Cin, int Cout, int D, int H,
                         int W, cudaStream_t st) {
   cudaMemsetAsync(dw, 0, (size_t)Cout * Cin * 27 * sizeof(float), st);
   if (db != nullptr) cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), st);
+  {
+    bool handled = false;
+    int rc = launch_conv3d_wgrad_tma(x, dy, dw, db, B, Cin, Cout, D, H, W, st, &handled);
+    if (handled) return rc;
+  }
   const int tiles_h = ceil_div(H, 4), tiles_w = ceil_div(W, 32);
   const long long groups = (long long)ceil_div(Cout, WG_CO) * Cin;
   if (groups > 65535) {

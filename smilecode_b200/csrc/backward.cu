@@ -502,6 +502,9 @@ int launch_upsample2x_bwd(const float* g, float* dx, int B, int C, int D, int H,
   return check_launch("upsample2x_bwd");
 }
 
+int launch_attn_bwd_dq_tma(const float* g, const float* q, const float* k, const float* rpb, float* dq, float* dl,
+                           float* drpb, int B, int D, int H, int W, float scale, cudaStream_t st, bool* handled);
+
 int launch_modet_attn_bwd(const float* g, const float* q, const float* k, const float* rpb, float* dq, float* dk,
                           float* drpb, float* dl_work, int B, int D, int H, int W, int heads, int hd, float scale,
                           cudaStream_t st) {
@@ -518,10 +521,18 @@ int launch_modet_attn_bwd(const float* g, const float* q, const float* k, const 
     }
   }
   dim3 grid(grid_for(total, 128, 32), B);
-  dim3 grid_q(grid_for((long long)D * H * W, 128, 16), B, heads);
-  attn_bwd_dq_kernel<<<grid_q, 128, 0, st>>>(g, q, k, rpb, dq, dl_work, drpb, D, H, W, heads, hd, scale);
-  int rc = check_launch("modet_attn_bwd(dq)");
-  if (rc) return rc;
+  int rc = SMILE_OK;
+  bool handled = false;
+  if (heads == 1 && hd == 6) {
+    rc = launch_attn_bwd_dq_tma(g, q, k, rpb, dq, dl_work, drpb, B, D, H, W, scale, st, &handled);
+    if (rc) return rc;
+  }
+  if (!handled) {
+    dim3 grid_q(grid_for((long long)D * H * W, 128, 16), B, heads);
+    attn_bwd_dq_kernel<<<grid_q, 128, 0, st>>>(g, q, k, rpb, dq, dl_work, drpb, D, H, W, heads, hd, scale);
+    rc = check_launch("modet_attn_bwd(dq)");
+    if (rc) return rc;
+  }
   attn_bwd_dk_kernel<<<grid, 128, 0, st>>>(dl_work, q, dk, D, H, W, heads, hd, scale);
   return check_launch("modet_attn_bwd(dk)");
 }

@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 
@@ -30,7 +31,10 @@ constexpr int TW = 32;        // voxels per tile row (one per lane)
 // boxes start a little further left than the 1-voxel halo: 2 voxels (48 B) for keys, 4 floats for flow.
 constexpr int KW = TW + 4;    // key row: voxels w0-2 .. w0+33
 constexpr int KOFF = 1;       // tile column of voxel (w - 1) for lane 0
-constexpr int FWP = 40;       // flow row: floats w0-4 .. w0+35 (160 B)
+// Flow rows are staged 64 floats wide although only w0-4 .. w0+35 is used: with a row pitch (and plane pitch) that
+// is a multiple of 32 banks, the bank of a compose-gather depends on the lane alone, not on which of the rows /
+// planes the lane picked, so the per-lane corner choice no longer causes ~2.6-way conflicts.
+constexpr int FWP = 64;
 constexpr int FOFF = 3;       // tile column of voxel (w - 1) for lane 0
 constexpr int HD = 6;         // head_dim of the reference configuration
 constexpr float kLog2e = 1.4426950408889634f;
@@ -56,9 +60,10 @@ struct Cfg {
   static constexpr int OFF_Q = OFF_K + NS * K_STRIDE;
   static constexpr int OFF_F = OFF_Q + NS * Q_STRIDE;
   static constexpr int OFF_BAR = OFF_F + NF * F_STRIDE;   // NS full barriers
-  static constexpr int OFF_CNT = OFF_BAR + 32;            // NS arrival counters
-  static constexpr int OFF_RPB = OFF_CNT + 32;            // 28 floats
-  static constexpr int OFF_SEG = OFF_RPB + 128;           // (MAXSEG + 1) segments
+  static constexpr int OFF_CNT = OFF_BAR + 32;            // NS "slot empty" barriers (one arrival per warp)
+  static constexpr int OFF_NEXT = OFF_CNT + 32;          // next stage to be issued (claimed with a CAS)
+  static constexpr int OFF_RPB = OFF_NEXT + 16;            // 3 tap planes x 12 floats (9 used; rows 16-byte aligned)
+  static constexpr int OFF_SEG = OFF_RPB + 192;           // (MAXSEG + 1) segments
   static constexpr int SMEM = OFF_SEG + (MAXSEG + 1) * (int)sizeof(Seg) + 64;
   static constexpr int THREADS = TH * 32;
 };
@@ -71,6 +76,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -82,6 +90,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint32_t lds_volatile(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t atom_cas_relaxed(uint32_t addr, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.relaxed.cta.shared::cta.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(addr), "r"(cmp), "r"(val) : "memory");
+  return old;
 }
 // A warp that runs ahead of its CTA must not burn issue slots polling (the arbiter favours it over
 // the warps it is waiting for): back off with nanosleep between polls.
@@ -98,18 +125,32 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-__device__ __forceinline__ uint32_t atom_add_acq_rel(uint32_t addr, uint32_t v) {
-  uint32_t old;
-  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
-  return old;
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking probe
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 
+// Packed fp32x2 arithmetic (SASS FFMA2 / FMUL2 / FADD2).  The "s" forms take a scalar that the hardware broadcasts
+// to both lanes (operand modifier R.F32), so no duplicated register pair is needed.
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
   float2 d;
   asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
       "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
       : "=f"(d.x), "=f"(d.y)
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fma2s(float2 a, float b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\tmov.b64 rc, {%5, %6};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b), "f"(c.x), "f"(c.y));
   return d;
 }
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
@@ -120,6 +161,14 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return d;
 }
+__device__ __forceinline__ float2 mul2s(float2 a, float b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b));
+  return d;
+}
 __device__ __forceinline__ float2 add2(float2 a, float2 b) {
   float2 d;
   asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
@@ -127,6 +176,27 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
       : "=f"(d.x), "=f"(d.y)
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return d;
+}
+__device__ __forceinline__ float2 add2s(float2 a, float b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b));
+  return d;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "sub.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ unsigned __smid() {
+  unsigned v;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+  return v;
 }
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
@@ -173,66 +243,82 @@ struct Dims {
   float rd, rh, rw;       // RN(1 / (S - 1))
 };
 
-// Softmax over the 27 logits (log2 domain) and expectation of the tap offsets (models.py:328-332).
+// Running softmax state of one in-flight voxel (log2 domain): maximum so far, sum of exponentials, and the
+// exponential-weighted sums that give the expected tap offset (models.py:328-332).  nd holds the sum of the FIRST tap
+// plane (offset -1 along depth) until the last plane turns it into  sum(last plane) - sum(first plane).
+struct Acc {
+  float m, s, nd, ah, aw;
+};
+
+// Fold the nine logits of one tap plane (index i = 3*(dy+1) + (dx+1)) into the running state.
 // L[] holds <q,k>; logit = qscale * <q,k> + rpb (rpb pre-scaled by log2 e) is formed here.
-__device__ __forceinline__ void softmax_expect27(float (&L)[27], const float* __restrict__ s_rpb, float qscale,
-                                                 float& od, float& oh, float& ow) {
-  const float2 sc2 = make_float2(qscale, qscale);  // scale * log2(e)
+// ROLE 0: first plane of the voxel (initialises A), 1: middle plane, 2: last plane (A.nd becomes the depth numerator).
+template <int ROLE>
+__device__ __forceinline__ void fold9(Acc& A, const float (&L)[9], const float* __restrict__ rpb9, float qscale) {
+  float l[9];
 #pragma unroll
-  for (int i = 0; i < 13; ++i) {
-    const float2 r = reinterpret_cast<const float2*>(s_rpb)[i];
-    const float2 v = fma2(make_float2(L[2 * i], L[2 * i + 1]), sc2, r);
-    L[2 * i] = v.x;
-    L[2 * i + 1] = v.y;
+  for (int i = 0; i < 2; ++i) {
+    const float4 r = reinterpret_cast<const float4*>(rpb9)[i];
+    const float2 v0 = fma2s(make_float2(L[4 * i], L[4 * i + 1]), qscale, make_float2(r.x, r.y));
+    const float2 v1 = fma2s(make_float2(L[4 * i + 2], L[4 * i + 3]), qscale, make_float2(r.z, r.w));
+    l[4 * i] = v0.x;
+    l[4 * i + 1] = v0.y;
+    l[4 * i + 2] = v1.x;
+    l[4 * i + 3] = v1.y;
   }
-  L[26] = fmaf(L[26], qscale, s_rpb[26]);
-  float m9[9];  // max as a depth-3 tree of 3-input max (13 instructions, no 13-deep dependent chain)
-#pragma unroll
-  for (int i = 0; i < 9; ++i) m9[i] = max3(L[3 * i], L[3 * i + 1], L[3 * i + 2]);
-  const float m = max3(max3(m9[0], m9[1], m9[2]), max3(m9[3], m9[4], m9[5]), max3(m9[6], m9[7], m9[8]));
-  const float2 nm = make_float2(-m, -m);
-  float p[27];
-#pragma unroll
-  for (int i = 0; i < 13; ++i) {
-    const float2 v = add2(make_float2(L[2 * i], L[2 * i + 1]), nm);
-    p[2 * i] = ex2(v.x);
-    p[2 * i + 1] = ex2(v.y);
+  l[8] = fmaf(L[8], qscale, rpb9[8]);
+  const float pm = max3(max3(l[0], l[1], l[2]), max3(l[3], l[4], l[5]), max3(l[6], l[7], l[8]));
+  float mn = pm, a = 0.f;
+  if (ROLE != 0) {
+    mn = fmaxf(A.m, pm);
+    a = ex2(A.m - mn);
   }
-  p[26] = ex2(L[26] - m);
-  float row[9], rw[9];
+  const float nm = -mn;
+  float e[9];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) {
-    row[i] = (p[3 * i] + p[3 * i + 2]) + p[3 * i + 1];
-    rw[i] = p[3 * i + 2] - p[3 * i];
+  for (int i = 0; i < 4; ++i) {
+    const float2 v = add2s(make_float2(l[2 * i], l[2 * i + 1]), nm);
+    e[2 * i] = ex2(v.x);
+    e[2 * i + 1] = ex2(v.y);
   }
-  const float c0 = (row[0] + row[1]) + row[2], c1 = (row[3] + row[4]) + row[5], c2 = (row[6] + row[7]) + row[8];
-  const float sum = (c0 + c2) + c1;
-  const float sd = c2 - c0;
-  const float sh = ((row[2] - row[0]) + (row[5] - row[3])) + (row[8] - row[6]);
-  const float sw = (((rw[0] + rw[1]) + (rw[2] + rw[3])) + ((rw[4] + rw[5]) + (rw[6] + rw[7]))) + rw[8];
-  const float inv = rcp_approx(sum);
-  od = sd * inv;
-  oh = sh * inv;
-  ow = sw * inv;
+  e[8] = ex2(l[8] + nm);
+  // rows 0 and 1 ride in the two lanes of the packed adds, row 2 is scalar
+  const float2 X = make_float2(e[0], e[3]), Y = make_float2(e[2], e[5]), Z = make_float2(e[1], e[4]);
+  const float2 R01 = add2(add2(X, Y), Z);
+  const float2 D01 = sub2(Y, X);
+  const float r2 = (e[6] + e[8]) + e[7], d2 = e[8] - e[6];
+  const float S = (R01.x + R01.y) + r2;
+  const float SH = r2 - R01.x;
+  const float SW = (D01.x + D01.y) + d2;
+  if (ROLE == 0) {
+    A.s = S;
+    A.nd = S;
+    A.ah = SH;
+    A.aw = SW;
+  } else {
+    A.s = fmaf(A.s, a, S);
+    A.nd = (ROLE == 1) ? A.nd * a : fmaf(-A.nd, a, S);
+    A.ah = fmaf(A.ah, a, SH);
+    A.aw = fmaf(A.aw, a, SW);
+  }
+  A.m = mn;
 }
 
-// One axis of a zeros-padded trilinear sample: corner indices clamped into the volume (so both
-// loads are always legal) and the weight of an out-of-volume corner forced to 0, which adds +-0
-// where torch's grid_sampler skips the corner (GridSampler.h:209-211) -- same sum.
-__device__ __forceinline__ void axis_corners(float c, int S, int& i0, int& i1, float& w0, float& w1) {
-  const float f = floorf(c);
+// One axis of a zeros-padded trilinear sample from global memory (the moved image): floor index, fraction,
+// corner indices clamped into the volume (so both loads are always legal) and in-bounds flags; an out-of-volume
+// corner contributes 0 like torch's grid_sampler (GridSampler.h:209-211).
+__device__ __forceinline__ void axis_corners(float c, int S, int& i0, int& i1, float& fr, bool& in0, bool& in1) {
   const int j0 = __float2int_rd(c), j1 = j0 + 1;
-  w1 = __fsub_rn(c, f);
-  w0 = __fsub_rn(__fadd_rn(f, 1.0f), c);
-  w0 = ((unsigned)j0 < (unsigned)S) ? w0 : 0.f;
-  w1 = ((unsigned)j1 < (unsigned)S) ? w1 : 0.f;
+  fr = (fabsf(c) < 1e9f) ? __fsub_rn(c, (float)j0) : 0.f;
+  in0 = (unsigned)j0 < (unsigned)S;
+  in1 = (unsigned)j1 < (unsigned)S;
   i0 = min(max(j0, 0), S - 1);
   i1 = min(max(j1, 0), S - 1);
 }
 
 template <int TH, int NS, bool COMPOSE>
-__device__ __forceinline__ void issue_stage(uint32_t sbase, const Seg* __restrict__ segs, int& pseg, int n,
-                                            const CUtensorMap* tm_k, const CUtensorMap* tm_q, const CUtensorMap* tm_f) {
+__device__ __noinline__ int issue_stage(uint32_t sbase, const Seg* __restrict__ segs, int pseg, int n,
+                                        const CUtensorMap* tm_k, const CUtensorMap* tm_q, const CUtensorMap* tm_f) {
   using C = Cfg<TH, NS>;
   constexpr int NF = C::NF;
   while (n >= segs[pseg + 1].s_begin) ++pseg;
@@ -240,13 +326,92 @@ __device__ __forceinline__ void issue_stage(uint32_t sbase, const Seg* __restric
   const int p = sg.d_a - 1 + (n - sg.s_begin);
   const int slot = n % NS, fslot = n % NF;
   const uint32_t full = sbase + C::OFF_BAR + 8 * slot;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   mbar_expect_tx(full, C::K_BYTES + C::Q_BYTES + (COMPOSE ? C::F_BYTES : 0));
   tma_load_4d(sbase + C::OFF_K + slot * C::K_STRIDE, tm_k, full, (sg.w0 - 2) * HD, sg.h0 - 1, p, sg.b);
   tma_load_4d(sbase + C::OFF_Q + slot * C::Q_STRIDE, tm_q, full, sg.w0 * HD, sg.h0, p + 1, sg.b);
   if (COMPOSE) tma_load_4d(sbase + C::OFF_F + fslot * C::F_STRIDE, tm_f, full, sg.w0 - 4, sg.h0 - 1, p, sg.b * 3);
+  return pseg;
 }
 
-template <int TH, int NS, bool TWOPASS, bool COMPOSE, bool MOVED, int MINB>
+// trilinear combination of eight corner values held as (z0, z1) lane pairs: x, then y, then z
+__device__ __forceinline__ float tri_combine(float2 y0x0, float2 y0x1, float2 y1x0, float2 y1x1, float fx, float fy,
+                                             float fz) {
+  const float gx = 1.0f - fx, gy = 1.0f - fy, gz = 1.0f - fz;
+  const float2 r0 = fma2s(y0x1, fx, mul2s(y0x0, gx));
+  const float2 r1 = fma2s(y1x1, fx, mul2s(y1x0, gx));
+  const float2 s = fma2s(r1, fy, mul2s(r0, gy));
+  return fmaf(s.y, fz, s.x * gz);
+}
+
+// Rare paths, kept out of line so the marching loop stays small in the instruction cache.
+struct F3 { float a, b, c; };
+// compose sample whose corner left the staged window (|w| == 1 up to rounding): exact global-memory gather
+__device__ __noinline__ F3 compose_sample_global(const float* __restrict__ fb, float cz, float cy, float cx, int D, int H,
+                                                 int W) {
+  TriSample s;
+  tri_setup(s, cz, cy, cx, D, H, W);
+  const int N = D * H * W;
+  F3 r;
+  r.a = tri_gather(s, fb);
+  r.b = tri_gather(s, fb + N);
+  r.c = tri_gather(s, fb + 2 * N);
+  return r;
+}
+struct Corners8 { float v[8]; float fz, fy, fx; };  // v: z0y0x0 z0y0x1 z0y1x0 z0y1x1 z1y0x0 ...
+// moved-image corners near the volume border (or of an inactive lane): clamped addresses, zeros outside.
+// Inlined: about a fifth of the warps of a 160-wide volume touch a border, and the loads must stay in flight
+// across the dot products like those of the interior path.
+__device__ __forceinline__ Corners8 moved_corners_border(const float* __restrict__ mb, float mz, float my, float mx, int D,
+                                                      int H, int W, bool active) {
+  int z0i, z1i, y0i, y1i, x0i, x1i;
+  bool zi0, zi1, yi0, yi1, xi0, xi1;
+  Corners8 c;
+  axis_corners(mz, D, z0i, z1i, c.fz, zi0, zi1);
+  axis_corners(my, H, y0i, y1i, c.fy, yi0, yi1);
+  axis_corners(mx, W, x0i, x1i, c.fx, xi0, xi1);
+  const float* r00 = mb + (z0i * H + y0i) * W;
+  const float* r01 = mb + (z0i * H + y1i) * W;
+  const float* r10 = mb + (z1i * H + y0i) * W;
+  const float* r11 = mb + (z1i * H + y1i) * W;
+  zi0 = zi0 && active;
+  zi1 = zi1 && active;
+  c.v[0] = (zi0 && yi0 && xi0) ? __ldg(r00 + x0i) : 0.f;
+  c.v[1] = (zi0 && yi0 && xi1) ? __ldg(r00 + x1i) : 0.f;
+  c.v[2] = (zi0 && yi1 && xi0) ? __ldg(r01 + x0i) : 0.f;
+  c.v[3] = (zi0 && yi1 && xi1) ? __ldg(r01 + x1i) : 0.f;
+  c.v[4] = (zi1 && yi0 && xi0) ? __ldg(r10 + x0i) : 0.f;
+  c.v[5] = (zi1 && yi0 && xi1) ? __ldg(r10 + x1i) : 0.f;
+  c.v[6] = (zi1 && yi1 && xi0) ? __ldg(r11 + x0i) : 0.f;
+  c.v[7] = (zi1 && yi1 && xi1) ? __ldg(r11 + x1i) : 0.f;
+  return c;
+}
+
+// Re-arming a ring slot is not tied to a particular warp: whoever notices first that every warp has released the slot
+// of stage n - NS claims stage n with a CAS on a shared counter and issues its TMA loads.  The check sits where warps
+// have time to spare (top of an iteration, and inside the wait for a stage that is not there yet), so the work lands
+// on warps that run ahead and not on the slowest one.  Called by lane 0 only.
+template <int TH, int NS, bool COMPOSE>
+__device__ __forceinline__ int try_issue(uint32_t sbase, const Seg* __restrict__ segs, int pseg, int total_stages,
+                                         const CUtensorMap* tm_k, const CUtensorMap* tm_q, const CUtensorMap* tm_f) {
+  using C = Cfg<TH, NS>;
+  const uint32_t next_addr = sbase + C::OFF_NEXT;
+  const uint32_t n = lds_volatile(next_addr);
+  if ((int)n < total_stages) {
+    const uint32_t k = n / NS;  // the slot (n % NS) is in its k-th use; its previous use was released in phase k - 1
+    if (mbar_test(sbase + C::OFF_CNT + 8 * (n - k * NS), (k - 1) & 1u)) {
+      if (atom_cas_relaxed(next_addr, n, n + 1) == n) pseg = issue_stage<TH, NS, COMPOSE>(sbase, segs, pseg, (int)n, tm_k, tm_q, tm_f);
+    }
+  }
+  return pseg;
+}
+
+// One iteration of the marching loop handles two things that are independent of each other:
+//   (1) the voxel whose 27 logits the PREVIOUS iteration completed: softmax, compose, stores, and the issue of the
+//       eight moved-image gathers;
+//   (2) the key plane of THIS iteration: wait for its TMA stage, 27 dot products, release the stage;
+//   (3) combine the gathers issued in (1) -- their latency is covered by (2), and (1) covers the TMA wait of (2).
+template <int TH, int NS, bool COMPOSE, bool MOVED, int MINB, bool DBG = false>
 __global__ void __launch_bounds__(TH * 32, MINB)
 fused_march_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_q,
                    const __grid_constant__ CUtensorMap tm_f, const float* __restrict__ rpb,
@@ -291,23 +456,24 @@ fused_march_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
     *s_nseg = ns;
     for (int i = 0; i < NS; ++i) {
       mbar_init(bar_full + 8 * i, 1);
-      reinterpret_cast<uint32_t*>(smem + C::OFF_CNT)[i] = 0;
+      mbar_init(cnt_base + 8 * i, TH);
+      if (i == 0) *reinterpret_cast<volatile uint32_t*>(smem + C::OFF_NEXT) = NS;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (tid < 28) s_rpb[tid] = (tid < 27 && rpb != nullptr) ? rpb[tid] * kLog2e : 0.f;
+  if (tid < 36) s_rpb[tid] = (tid % 12 < 9 && rpb != nullptr) ? rpb[(tid / 12) * 9 + tid % 12] * kLog2e : 0.f;
   __syncthreads();
   const int nseg = *s_nseg;
   const int total_stages = segs[nseg].s_begin;
   int pseg = 0;  // segment cursor of the TMA issue path (per warp; only lane 0 uses it)
   if (tid == 0) {
-    for (int n = 0; n < NS && n < total_stages; ++n) issue_stage<TH, NS, COMPOSE>(sbase, segs, pseg, n, &tm_k, &tm_q, &tm_f);
+    for (int n = 0; n < NS && n < total_stages; ++n) pseg = issue_stage<TH, NS, COMPOSE>(sbase, segs, pseg, n, &tm_k, &tm_q, &tm_f);
   }
 
   int slot = 0, fslot = 0, it = 0;
   uint32_t par = 0;
-  bool ready = false;
+  long long dbg_wait = 0, dbg_t0 = DBG ? clock64() : 0;
+  int dbg_fail = 0;
   // per-thread shared-memory bases (bytes)
   const uint8_t* q_thr = smem + C::OFF_Q + (r * TW + lane) * (HD * 4);
   const uint8_t* k_thr = smem + C::OFF_K + (r * KW + lane + KOFF) * (HD * 4);
@@ -322,51 +488,36 @@ fused_march_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
     const float* fb = COMPOSE ? flow_in + (long long)sg.b * 3 * N : nullptr;
     const float* mb = MOVED ? moving + (long long)sg.b * Cmov * N : nullptr;
     float* mvb = MOVED ? moved + (long long)sg.b * Cmov * N : nullptr;
-    int vo = (sg.d_a - 2) * HW + h * W + wg;  // linear offset of the voxel that completes at the current stage
-    int f_m2 = 0, f_m1 = 0;                  // flow ring byte offsets of planes p-2, p-1
+    int vo = (sg.d_a - 3) * HW + h * W + wg;  // linear offset of the voxel handled by part (1) of the current iteration
+    float vf = (float)(sg.d_a - 3);            // its depth
+    int f_m3 = 0, f_m2 = 0, f_m1 = 0;          // flow ring byte offsets of the stages it-3, it-2, it-1
 
     float2 q[3][3];
-    float lg[3][27];
+    Acc acc[3];
 #pragma unroll
-    for (int s = 0; s < 3; ++s)
+    for (int s = 0; s < 3; ++s) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) q[s][i] = make_float2(0.f, 0.f);
+      acc[s].m = acc[s].s = acc[s].nd = acc[s].ah = acc[s].aw = 0.f;
+    }
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f;  // attention output of the voxel completed by the previous iteration
 
-    const int nsteps = sg.L + 2;
-    for (int z0 = 0; z0 < nsteps; z0 += 3) {
+    const int nsteps = sg.L + 2;  // key planes of this segment; iteration nsteps only finishes the last voxel
+    for (int z0 = 0; z0 <= nsteps; z0 += 3) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         const int z = z0 + j;
-        if (z >= nsteps) break;
-        const int sN = j, sM = (j + 2) % 3, sO = (j + 1) % 3;  // new (tap plane 0), middle (1), oldest (2: completes)
-        if (!ready) mbar_wait(bar_full + 8 * slot, par);
+        if (z > nsteps) break;
+        // storage roles of the three in-flight voxels: new (tap plane 0), middle (1), oldest (2: completes)
+        const int sN = j, sM = (j + 2) % 3, sO = (j + 1) % 3;
+        if (lane == 0) pseg = try_issue<TH, NS, COMPOSE>(sbase, segs, pseg, total_stages, &tm_k, &tm_q, &tm_f);
+        __syncwarp();
+        float2 mv[4];            // moved-image corners as (z0, z1) pairs: y0x0, y0x1, y1x0, y1x1
+        float mfx = 0.f, mfy = 0.f, mfz = 0.f;
+        bool pend = false;
 
-        // query of the voxel that starts at this plane (depth p + 1), scaled into the log2 domain
-        {
-          const float2* qs = reinterpret_cast<const float2*>(q_thr + slot * C::Q_STRIDE);
-          q[sN][0] = qs[0];
-          q[sN][1] = qs[1];
-          q[sN][2] = qs[2];
-        }
-        const float2* ks = reinterpret_cast<const float2*>(k_thr + slot * C::K_STRIDE);
-        // pass 1: the nine taps that complete the oldest voxel (TWOPASS), or all 27 products of the plane
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          const float2* kr = ks + ((i / 3) * KW + (i % 3)) * 3;
-          const float2 k0 = kr[0], k1 = kr[1], k2 = kr[2];
-          lg[sO][18 + i] = dot6(q[sO], k0, k1, k2);
-          if (!TWOPASS) {
-            lg[sN][i] = dot6(q[sN], k0, k1, k2);
-            lg[sM][9 + i] = dot6(q[sM], k0, k1, k2);
-          }
-        }
-        const int f_0 = fslot * C::F_STRIDE;
-
-        float fo0 = 0.f, fo1 = 0.f, fo2 = 0.f;  // flow_out of the completed voxel (for the moved sample)
-        if (z >= 2) {
-          const int v = sg.d_a - 2 + z;  // completed voxel depth
-          float w0, w1, w2;
-          softmax_expect27(lg[sO], s_rpb, qscale, w0, w1, w2);
+        // ---- (1) voxel completed by the previous iteration
+        if (z >= 3) {
           if (!COMPOSE) {
             if (valid) {
               ob[vo] = w0;
@@ -374,139 +525,159 @@ fused_march_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
               ob[vo + 2 * N] = w2;
             }
           } else {
-            const float vf = (float)v;
             const float cz = st_coord_fast(vf, w0, dm.dm1, dm.rd);
             const float cy = st_coord_fast(hf, w1, dm.hm1, dm.rh);
             const float cx = st_coord_fast(wf, w2, dm.wm1, dm.rw);
-            const float z0f = floorf(cz), y0f = floorf(cy), x0f = floorf(cx);
-            const int lz = __float2int_rd(cz) - (v - 1), ly = __float2int_rd(cy) - (h - 1),
-                      lx = __float2int_rd(cx) - (wg - 1);
+            // floor(c) is idx - 1 or idx when the sample stays in the staged window (exact float compares)
+            const bool bz = cz >= vf, by = cy >= hf, bx = cx >= wf;
+            const bool inwin = (cz >= vf - 1.0f) && (cz < vf + 1.0f) && (cy >= hf - 1.0f) && (cy < hf + 1.0f) &&
+                               (cx >= wf - 1.0f) && (cx < wf + 1.0f);
             float f0, f1, f2;
-            if (((unsigned)lz <= 1u) && ((unsigned)ly <= 1u) && ((unsigned)lx <= 1u)) {
-              const float wz1 = __fsub_rn(cz, z0f), wy1 = __fsub_rn(cy, y0f), wx1 = __fsub_rn(cx, x0f);
-              const float wz0 = __fsub_rn(__fadd_rn(z0f, 1.0f), cz), wy0 = __fsub_rn(__fadd_rn(y0f, 1.0f), cy),
-                          wx0 = __fsub_rn(__fadd_rn(x0f, 1.0f), cx);
-              const float w00 = __fmul_rn(wx0, wy0), w10 = __fmul_rn(wx1, wy0), w01 = __fmul_rn(wx0, wy1),
-                          w11 = __fmul_rn(wx1, wy1);
-              const float wa0 = __fmul_rn(w00, wz0), wa1 = __fmul_rn(w10, wz0), wa2 = __fmul_rn(w01, wz0),
-                          wa3 = __fmul_rn(w11, wz0), wb0 = __fmul_rn(w00, wz1), wb1 = __fmul_rn(w10, wz1),
-                          wb2 = __fmul_rn(w01, wz1), wb3 = __fmul_rn(w11, wz1);
-              const int o = (ly * FWP + lx) * 4;
-              const float* pa = reinterpret_cast<const float*>(f_thr + (lz ? f_m1 : f_m2) + o);
-              const float* pb = reinterpret_cast<const float*>(f_thr + (lz ? f_0 : f_m1) + o);
-              float acc[3];
-#pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                const float* a = pa + c * C::F_PLANE;
-                const float* bq = pb + c * C::F_PLANE;
-                float t = __fmul_rn(a[0], wa0);
-                t = __fadd_rn(t, __fmul_rn(a[1], wa1));
-                t = __fadd_rn(t, __fmul_rn(a[FWP], wa2));
-                t = __fadd_rn(t, __fmul_rn(a[FWP + 1], wa3));
-                t = __fadd_rn(t, __fmul_rn(bq[0], wb0));
-                t = __fadd_rn(t, __fmul_rn(bq[1], wb1));
-                t = __fadd_rn(t, __fmul_rn(bq[FWP], wb2));
-                t = __fadd_rn(t, __fmul_rn(bq[FWP + 1], wb3));
-                acc[c] = t;
-              }
-              f0 = acc[0];
-              f1 = acc[1];
-              f2 = acc[2];
-            } else {
-              // a corner left the staged window (|w| == 1 up to rounding): exact global-memory gather
+            {
+              // shared-memory addresses are inside the staged window whatever the coordinates are
+              const float fz = __fsub_rn(cz, bz ? vf : vf - 1.0f), fy = __fsub_rn(cy, by ? hf : hf - 1.0f),
+                          fx = __fsub_rn(cx, bx ? wf : wf - 1.0f);
+              const int o = (by ? FWP * 4 : 0) + (bx ? 4 : 0);
+              const float* pa = reinterpret_cast<const float*>(f_thr + (bz ? f_m2 : f_m3) + o);
+              const float* pb = reinterpret_cast<const float*>(f_thr + (bz ? f_m1 : f_m2) + o);
+              const float gx = 1.0f - fx, gy = 1.0f - fy, gz = 1.0f - fz;
+              // channels 0 and 1 ride in the two lanes of the packed ops
+              const float* pa1 = pa + C::F_PLANE;
+              const float* pb1 = pb + C::F_PLANE;
+              const float2 a00 = make_float2(pa[0], pa1[0]), a01 = make_float2(pa[1], pa1[1]),
+                           a10 = make_float2(pa[FWP], pa1[FWP]), a11 = make_float2(pa[FWP + 1], pa1[FWP + 1]),
+                           b00 = make_float2(pb[0], pb1[0]), b01 = make_float2(pb[1], pb1[1]),
+                           b10 = make_float2(pb[FWP], pb1[FWP]), b11 = make_float2(pb[FWP + 1], pb1[FWP + 1]);
+              const float2 ra0 = fma2s(a01, fx, mul2s(a00, gx)), ra1 = fma2s(a11, fx, mul2s(a10, gx)),
+                           rb0 = fma2s(b01, fx, mul2s(b00, gx)), rb1 = fma2s(b11, fx, mul2s(b10, gx));
+              const float2 sa = fma2s(ra1, fy, mul2s(ra0, gy)), sb = fma2s(rb1, fy, mul2s(rb0, gy));
+              const float2 t01 = fma2s(sb, fz, mul2s(sa, gz));
+              f0 = t01.x;
+              f1 = t01.y;
+              // channel 2: lanes = (plane a, plane b)
+              const float* pa2 = pa + 2 * C::F_PLANE;
+              const float* pb2 = pb + 2 * C::F_PLANE;
+              f2 = tri_combine(make_float2(pa2[0], pb2[0]), make_float2(pa2[1], pb2[1]),
+                               make_float2(pa2[FWP], pb2[FWP]), make_float2(pa2[FWP + 1], pb2[FWP + 1]), fx, fy, fz);
+            }
+            if (!inwin) {
               f0 = f1 = f2 = 0.f;
               if (valid) {
-                TriSample s;
-                tri_setup(s, cz, cy, cx, D, H, W);
-                f0 = tri_gather(s, fb);
-                f1 = tri_gather(s, fb + N);
-                f2 = tri_gather(s, fb + 2 * N);
+                const F3 g = compose_sample_global(fb, cz, cy, cx, D, H, W);
+                f0 = g.a;
+                f1 = g.b;
+                f2 = g.c;
               }
             }
             f0 = __fmul_rn(post, __fadd_rn(f0, w0));
             f1 = __fmul_rn(post, __fadd_rn(f1, w1));
             f2 = __fmul_rn(post, __fadd_rn(f2, w2));
-            fo0 = f0;
-            fo1 = f1;
-            fo2 = f2;
             if (valid) {
               ob[vo] = f0;
               ob[vo + N] = f1;
               ob[vo + 2 * N] = f2;
             }
-          }
-        }
-
-        // moved = T(moving, flow_out): addresses + weights now, the eight loads fly during pass 2
-        float mval[8], mwt[8];
-        const bool do_moved = MOVED && COMPOSE && (z >= 2) && valid;
-        if (MOVED) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) mval[c] = mwt[c] = 0.f;
-        }
-        if (do_moved) {
-          int z0i, z1i, y0i, y1i, x0i, x1i;
-          float uz0, uz1, uy0, uy1, ux0, ux1;
-          axis_corners(st_coord_fast((float)(sg.d_a - 2 + z), fo0, dm.dm1, dm.rd), D, z0i, z1i, uz0, uz1);
-          axis_corners(st_coord_fast(hf, fo1, dm.hm1, dm.rh), H, y0i, y1i, uy0, uy1);
-          axis_corners(st_coord_fast(wf, fo2, dm.wm1, dm.rw), W, x0i, x1i, ux0, ux1);
-          const float u00 = __fmul_rn(ux0, uy0), u10 = __fmul_rn(ux1, uy0), u01 = __fmul_rn(ux0, uy1),
-                      u11 = __fmul_rn(ux1, uy1);
-          mwt[0] = __fmul_rn(u00, uz0); mwt[1] = __fmul_rn(u10, uz0); mwt[2] = __fmul_rn(u01, uz0);
-          mwt[3] = __fmul_rn(u11, uz0); mwt[4] = __fmul_rn(u00, uz1); mwt[5] = __fmul_rn(u10, uz1);
-          mwt[6] = __fmul_rn(u01, uz1); mwt[7] = __fmul_rn(u11, uz1);
-          const unsigned r00 = (unsigned)((z0i * H + y0i) * W), r01 = (unsigned)((z0i * H + y1i) * W),
-                         r10 = (unsigned)((z1i * H + y0i) * W), r11 = (unsigned)((z1i * H + y1i) * W);
-          const unsigned ux0i = (unsigned)x0i, ux1i = (unsigned)x1i;
-          mval[0] = __ldg(mb + (r00 + ux0i)); mval[1] = __ldg(mb + (r00 + ux1i));
-          mval[2] = __ldg(mb + (r01 + ux0i)); mval[3] = __ldg(mb + (r01 + ux1i));
-          mval[4] = __ldg(mb + (r10 + ux0i)); mval[5] = __ldg(mb + (r10 + ux1i));
-          mval[6] = __ldg(mb + (r11 + ux0i)); mval[7] = __ldg(mb + (r11 + ux1i));
-        }
-
-        // pass 2: first nine taps of the new voxel, middle nine of the previous one
-#pragma unroll
-        for (int i = 0; i < (TWOPASS ? 9 : 0); ++i) {
-          const float2* kr = ks + ((i / 3) * KW + (i % 3)) * 3;
-          const float2 k0 = kr[0], k1 = kr[1], k2 = kr[2];
-          lg[sN][i] = dot6(q[sN], k0, k1, k2);
-          lg[sM][9 + i] = dot6(q[sM], k0, k1, k2);
-        }
-
-        if (do_moved) {
-          float t = __fmul_rn(mval[0], mwt[0]);
-#pragma unroll
-          for (int c = 1; c < 8; ++c) t = __fadd_rn(t, __fmul_rn(mval[c], mwt[c]));
-          mvb[vo] = t;
-        }
-
-        // release the slot; the warp that arrives last re-arms it with the stage NS steps ahead
-        __syncwarp();
-        if (lane == 0) {
-          const uint32_t prev = atom_add_acq_rel(cnt_base + 4 * slot, 1u);
-          if (prev == TH - 1) {
-            reinterpret_cast<volatile uint32_t*>(smem + C::OFF_CNT)[slot] = 0;
-            const int n = it + NS;
-            if (n < total_stages) {
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              issue_stage<TH, NS, COMPOSE>(sbase, segs, pseg, n, &tm_k, &tm_q, &tm_f);
+            if (MOVED) {
+              // moved = T(moving, flow_out): issue the eight gathers now, combine them after the dot products
+              const float mz = st_coord_fast(vf, f0, dm.dm1, dm.rd);
+              const float my = st_coord_fast(hf, f1, dm.hm1, dm.rh);
+              const float mx = st_coord_fast(wf, f2, dm.wm1, dm.rw);
+              const int jz = __float2int_rd(mz), jy = __float2int_rd(my), jx = __float2int_rd(mx);
+              const bool interior = valid && ((unsigned)jz < (unsigned)(D - 1)) && ((unsigned)jy < (unsigned)(H - 1)) &&
+                                    ((unsigned)jx < (unsigned)(W - 1));
+              if (__all_sync(0xffffffffu, interior)) {
+                mfz = __fsub_rn(mz, (float)jz);
+                mfy = __fsub_rn(my, (float)jy);
+                mfx = __fsub_rn(mx, (float)jx);
+                const float* p0 = mb + ((jz * H + jy) * W + jx);
+                const float* p1 = p0 + HW;
+                mv[0] = make_float2(__ldg(p0), __ldg(p1));
+                mv[1] = make_float2(__ldg(p0 + 1), __ldg(p1 + 1));
+                mv[2] = make_float2(__ldg(p0 + W), __ldg(p1 + W));
+                mv[3] = make_float2(__ldg(p0 + W + 1), __ldg(p1 + W + 1));
+              } else {
+                const Corners8 c = moved_corners_border(mb, mz, my, mx, D, H, W, valid);
+                mv[0] = make_float2(c.v[0], c.v[4]);
+                mv[1] = make_float2(c.v[1], c.v[5]);
+                mv[2] = make_float2(c.v[2], c.v[6]);
+                mv[3] = make_float2(c.v[3], c.v[7]);
+                mfz = c.fz;
+                mfy = c.fy;
+                mfx = c.fx;
+              }
+              pend = true;
             }
           }
         }
-        ++it;
-        vo += HW;
-        f_m2 = f_m1;
-        f_m1 = f_0;
-        if (++slot == NS) {
-          slot = 0;
-          par ^= 1u;
+
+        // ---- (2) key plane of this iteration
+        if (z < nsteps) {
+          {
+            const long long t0 = DBG ? clock64() : 0;
+            if (!mbar_try_wait_hint(bar_full + 8 * slot, par, 200)) {
+              do {  // the stage is late: use the time to re-arm slots other warps have released
+                if (lane == 0) pseg = try_issue<TH, NS, COMPOSE>(sbase, segs, pseg, total_stages, &tm_k, &tm_q, &tm_f);
+                __syncwarp();
+              } while (!mbar_try_wait_hint(bar_full + 8 * slot, par, 200));
+              if (DBG) ++dbg_fail;
+            }
+            if (DBG) dbg_wait += clock64() - t0;
+          }
+          {
+            const float2* qs = reinterpret_cast<const float2*>(q_thr + slot * C::Q_STRIDE);
+            q[sN][0] = qs[0];
+            q[sN][1] = qs[1];
+            q[sN][2] = qs[2];
+          }
+          const float2* ks = reinterpret_cast<const float2*>(k_thr + slot * C::K_STRIDE);
+          // tap plane 2 of the oldest voxel (completes it), 1 of the middle one, 0 of the new one
+          float LO[9], LM[9], LN[9];
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            const float2* kr = ks + ((i / 3) * KW + (i % 3)) * 3;
+            const float2 k0 = kr[0], k1 = kr[1], k2 = kr[2];
+            LO[i] = dot6(q[sO], k0, k1, k2);
+            LN[i] = dot6(q[sN], k0, k1, k2);
+            LM[i] = dot6(q[sM], k0, k1, k2);
+          }
+          // this warp is done with the key/query slot
+          __syncwarp();
+          if (lane == 0) mbar_arrive(cnt_base + 8 * slot);
+          // online softmax: the three folds are independent of each other
+          fold9<0>(acc[sN], LN, s_rpb, qscale);
+          fold9<1>(acc[sM], LM, s_rpb + 12, qscale);
+          fold9<2>(acc[sO], LO, s_rpb + 24, qscale);
+          {
+            const float inv = rcp_approx(acc[sO].s);
+            w0 = acc[sO].nd * inv;
+            w1 = acc[sO].ah * inv;
+            w2 = acc[sO].aw * inv;
+          }
+          ++it;
+          f_m3 = f_m2;
+          f_m2 = f_m1;
+          f_m1 = fslot * C::F_STRIDE;
+          if (++slot == NS) {
+            slot = 0;
+            par ^= 1u;
+          }
+          if (++fslot == NF) fslot = 0;
         }
-        if (++fslot == NF) fslot = 0;
-        // poll the next stage's barrier now so its ~90-cycle query latency hides behind this step's tail
-        ready = (it < total_stages) && mbar_try_wait(bar_full + 8 * slot, par);
+
+        // ---- (3) finish the moved sample of part (1)
+        if (MOVED && pend) {
+          const float t = tri_combine(mv[0], mv[1], mv[2], mv[3], mfx, mfy, mfz);
+          if (valid) mvb[vo] = t;
+        }
+        vo += HW;
+        vf += 1.0f;
       }
     }
   }
+  if (DBG && lane == 0 && (blockIdx.x % 59 == 0))
+    printf("cta %3d warp %d sm %2d: stages %3d total %7lld cyc, barrier wait %7lld cyc (%4.1f%%), first try failed %3d\n",
+           (int)blockIdx.x, r, (int)__smid(), total_stages, clock64() - dbg_t0, dbg_wait,
+           100.0 * (double)dbg_wait / (double)(clock64() - dbg_t0), dbg_fail);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -538,12 +709,12 @@ bool encode4(CUtensorMap* map, const void* base, const cuuint64_t (&dims)[4], co
   return true;
 }
 
-template <int TH, int NS, bool TWOPASS, bool COMPOSE, bool MOVED, int MINB>
+template <int TH, int NS, bool COMPOSE, bool MOVED, int MINB, bool DBG = false>
 int launch_cfg(const CUtensorMap& mk, const CUtensorMap& mq, const CUtensorMap& mf, const float* rpb, const float* flow_in,
                const float* moving, float* out0, float* moved, const Dims& dm, int grid, float qscale, float post, int Cmov,
                cudaStream_t st) {
   using C = Cfg<TH, NS>;
-  auto kern = fused_march_kernel<TH, NS, TWOPASS, COMPOSE, MOVED, MINB>;
+  auto kern = fused_march_kernel<TH, NS, COMPOSE, MOVED, MINB, DBG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
   if (e != cudaSuccess) {
     set_error("modet_fused(TMA): cannot reserve %d B of shared memory: %s", C::SMEM, cudaGetErrorString(e));
@@ -562,6 +733,7 @@ int launch_modet_attn_tma(const float* q, const float* k, const float* rpb, cons
                           int Cmov, cudaStream_t st, bool* handled) {
   *handled = false;
   constexpr int TH = 8;
+  static_assert((TH & (TH - 1)) == 0, "the slot arrival counter test needs a power-of-two warp count");
   const bool compose = flow_in != nullptr;
   if (W % 4 != 0 || D < 2 || H < 2 || W < 2) return SMILE_OK;
   if (moved != nullptr && Cmov != 1) return SMILE_OK;  // the fused sampler handles the single-channel moving image
@@ -575,7 +747,7 @@ int launch_modet_attn_tma(const float* q, const float* k, const float* rpb, cons
   dm.ncol_w = ceil_div(W, TW);
   dm.total_units = (long long)B * dm.ncol_h * dm.ncol_w * D;
   static const int variant_for_slots = [] { const char* e = getenv("SMILE_FUSED_VARIANT"); return e ? atoi(e) : 0; }();
-  long long slots = (variant_for_slots == 4 ? 3LL : 2LL) * kNumSMs;
+  long long slots = (variant_for_slots == 3 ? 3LL : 2LL) * kNumSMs;
   long long per = ceil_div_ll(dm.total_units, slots);
   if (per < 4) per = 4;                                        // amortise the two halo planes of a segment
   if (per > (long long)(MAXSEG - 2) * D) per = (long long)(MAXSEG - 2) * D;  // bound the per-CTA segment table
@@ -599,23 +771,27 @@ int launch_modet_attn_tma(const float* q, const float* k, const float* rpb, cons
     mf = mq;
   }
   const float qscale = scale * kLog2e;
-#define SMILE_LAUNCH(NSV, TP, MB)                                                                                            \
+#define SMILE_LAUNCH(NSV, MB)                                                                                                \
   do {                                                                                                                    \
     if (!compose)                                                                                                         \
-      return launch_cfg<TH, NSV, TP, false, false, MB>(mk, mq, mf, rpb, nullptr, nullptr, w_out, nullptr, dm, grid, qscale,   \
+      return launch_cfg<TH, NSV, false, false, MB>(mk, mq, mf, rpb, nullptr, nullptr, w_out, nullptr, dm, grid, qscale,   \
                                                    1.0f, 0, st);                                                          \
     if (moved != nullptr)                                                                                                 \
-      return launch_cfg<TH, NSV, TP, true, true, MB>(mk, mq, mf, rpb, flow_in, moving, flow_out, moved, dm, grid, qscale,     \
+      return launch_cfg<TH, NSV, true, true, MB>(mk, mq, mf, rpb, flow_in, moving, flow_out, moved, dm, grid, qscale,     \
                                                  post, Cmov, st);                                                         \
-    return launch_cfg<TH, NSV, TP, true, false, MB>(mk, mq, mf, rpb, flow_in, nullptr, flow_out, nullptr, dm, grid, qscale,   \
+    return launch_cfg<TH, NSV, true, false, MB>(mk, mq, mf, rpb, flow_in, nullptr, flow_out, nullptr, dm, grid, qscale,   \
                                                 post, 0, st);                                                             \
   } while (0)
   static const int variant = [] { const char* e = getenv("SMILE_FUSED_VARIANT"); return e ? atoi(e) : 0; }();
   switch (variant) {  // tuning knob for profiling runs; 0 is the production configuration
-    case 1: SMILE_LAUNCH(4, false, 2);
-    case 2: SMILE_LAUNCH(3, true, 2);
-    case 4: SMILE_LAUNCH(3, false, 3);
-    default: SMILE_LAUNCH(3, false, 2);
+    case 1: SMILE_LAUNCH(4, 2);
+    case 3: SMILE_LAUNCH(3, 3);
+    case 9:  // per-warp barrier-wait timing printed from the kernel (profiling aid)
+      if (compose && moved != nullptr)
+        return launch_cfg<TH, 3, true, true, 2, true>(mk, mq, mf, rpb, flow_in, moving, flow_out, moved, dm, grid, qscale, post,
+                                                      Cmov, st);
+      SMILE_LAUNCH(3, 2);
+    default: SMILE_LAUNCH(3, 2);
   }
 #undef SMILE_LAUNCH
 }

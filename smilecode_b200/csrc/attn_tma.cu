@@ -76,8 +76,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+// arrival by one lane of a converged warp, as a predicated instruction (no divergent branch)
+__device__ __forceinline__ void mbar_arrive_lane0(uint32_t bar, int lane) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\t@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(bar), "r"(lane)
+               : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -488,7 +490,9 @@ fused_march_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
     const float* fb = COMPOSE ? flow_in + (long long)sg.b * 3 * N : nullptr;
     const float* mb = MOVED ? moving + (long long)sg.b * Cmov * N : nullptr;
     float* mvb = MOVED ? moved + (long long)sg.b * Cmov * N : nullptr;
-    int vo = (sg.d_a - 3) * HW + h * W + wg;  // linear offset of the voxel handled by part (1) of the current iteration
+    // linear offset of the voxel handled by part (1) of the current iteration; unsigned so that an address is one
+    // IMAD.WIDE.U32 (wraps harmlessly for the not-yet-valid voxels in front of the segment, which are never stored)
+    unsigned vo = (unsigned)((sg.d_a - 3) * HW + h * W + wg);
     float vf = (float)(sg.d_a - 3);            // its depth
     int f_m3 = 0, f_m2 = 0, f_m1 = 0;          // flow ring byte offsets of the stages it-3, it-2, it-1
 
@@ -510,8 +514,10 @@ fused_march_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
         if (z > nsteps) break;
         // storage roles of the three in-flight voxels: new (tap plane 0), middle (1), oldest (2: completes)
         const int sN = j, sM = (j + 2) % 3, sO = (j + 1) % 3;
-        if (lane == 0) pseg = try_issue<TH, NS, COMPOSE>(sbase, segs, pseg, total_stages, &tm_k, &tm_q, &tm_f);
-        __syncwarp();
+        if (((it ^ r) & 3) == 0) {  // two of the eight warps look per step; warps blocked on a late stage look as well
+          if (lane == 0) pseg = try_issue<TH, NS, COMPOSE>(sbase, segs, pseg, total_stages, &tm_k, &tm_q, &tm_f);
+          __syncwarp();
+        }
         float2 mv[4];            // moved-image corners as (z0, z1) pairs: y0x0, y0x1, y1x0, y1x1
         float mfx = 0.f, mfy = 0.f, mfz = 0.f;
         bool pend = false;
@@ -521,8 +527,8 @@ fused_march_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
           if (!COMPOSE) {
             if (valid) {
               ob[vo] = w0;
-              ob[vo + N] = w1;
-              ob[vo + 2 * N] = w2;
+              ob[vo + (unsigned)N] = w1;
+              ob[vo + 2u * (unsigned)N] = w2;
             }
           } else {
             const float cz = st_coord_fast(vf, w0, dm.dm1, dm.rd);
@@ -574,8 +580,8 @@ fused_march_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
             f2 = __fmul_rn(post, __fadd_rn(f2, w2));
             if (valid) {
               ob[vo] = f0;
-              ob[vo + N] = f1;
-              ob[vo + 2 * N] = f2;
+              ob[vo + (unsigned)N] = f1;
+              ob[vo + 2u * (unsigned)N] = f2;
             }
             if (MOVED) {
               // moved = T(moving, flow_out): issue the eight gathers now, combine them after the dot products
@@ -589,12 +595,13 @@ fused_march_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
                 mfz = __fsub_rn(mz, (float)jz);
                 mfy = __fsub_rn(my, (float)jy);
                 mfx = __fsub_rn(mx, (float)jx);
-                const float* p0 = mb + ((jz * H + jy) * W + jx);
-                const float* p1 = p0 + HW;
-                mv[0] = make_float2(__ldg(p0), __ldg(p1));
-                mv[1] = make_float2(__ldg(p0 + 1), __ldg(p1 + 1));
-                mv[2] = make_float2(__ldg(p0 + W), __ldg(p1 + W));
-                mv[3] = make_float2(__ldg(p0 + W + 1), __ldg(p1 + W + 1));
+                const unsigned i00 = (unsigned)((jz * H + jy) * W + jx), i01 = i00 + (unsigned)W,
+                               i10 = i00 + (unsigned)HW, i11 = i10 + (unsigned)W;
+                const float *p00 = mb + i00, *p01 = mb + i01, *p10 = mb + i10, *p11 = mb + i11;
+                mv[0] = make_float2(__ldg(p00), __ldg(p10));
+                mv[1] = make_float2(__ldg(p00 + 1), __ldg(p10 + 1));
+                mv[2] = make_float2(__ldg(p01), __ldg(p11));
+                mv[3] = make_float2(__ldg(p01 + 1), __ldg(p11 + 1));
               } else {
                 const Corners8 c = moved_corners_border(mb, mz, my, mx, D, H, W, valid);
                 mv[0] = make_float2(c.v[0], c.v[4]);
@@ -642,7 +649,7 @@ fused_march_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
           }
           // this warp is done with the key/query slot
           __syncwarp();
-          if (lane == 0) mbar_arrive(cnt_base + 8 * slot);
+          mbar_arrive_lane0(cnt_base + 8 * slot, lane);
           // online softmax: the three folds are independent of each other
           fold9<0>(acc[sN], LN, s_rpb, qscale);
           fold9<1>(acc[sM], LM, s_rpb + 12, qscale);
@@ -669,7 +676,7 @@ fused_march_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
           const float t = tri_combine(mv[0], mv[1], mv[2], mv[3], mfx, mfy, mfz);
           if (valid) mvb[vo] = t;
         }
-        vo += HW;
+        vo += (unsigned)HW;
         vf += 1.0f;
       }
     }

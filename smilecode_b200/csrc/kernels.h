@@ -28,6 +28,9 @@ int launch_proj_ln(const float* feat, const float* weight, const float* bias, co
 int launch_conv3d(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
                   double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
                   cudaStream_t st);
+int launch_conv3d_tma_flat(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
+                           double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
+                           cudaStream_t st, bool* handled);
 int launch_in_finalize(const float* raw, const double* stats, float* out, float* pooled, int B, int C, int D, int H,
                        int W, float eps, cudaStream_t st);
 int launch_cwm_fuse(const float* fields, const float* logits, float* out, int B, int F, long long N, cudaStream_t st);

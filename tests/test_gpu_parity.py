@@ -152,6 +152,27 @@ def test_conv_norm_on_load_and_pool(ops):
     assert (pooled.cpu() - torch.nn.functional.avg_pool3d(ref, 2)).abs().max() <= 2e-5
 
 
+@pytest.mark.parametrize("cin,cout,shape", [(8, 16, (5, 7, 20)), (12, 24, (4, 5, 28)), (16, 32, (6, 10, 40)),
+                                            (4, 8, (3, 5, 56)), (8, 16, (9, 11, 80)), (8, 4, (2, 3, 112))])
+def test_conv_flat_tiles_norm_on_load(ops, cin, cout, shape):
+    """Full-row ("flat") tiles of the TMA conv (W = 20/28/40/56/80/112): partial tiles in H and D, odd channel
+    counts, producer InstanceNorm + LeakyReLU applied on load, statistics of the raw output."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, cin, *shape, generator=g)
+    w1 = torch.randn(cin, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5
+    w2 = torch.randn(cout, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5
+    b1, b2 = torch.randn(cin, generator=g) * 0.1, torch.randn(cout, generator=g) * 0.1
+    r1 = orc.conv3(x, w1, b1)
+    ref = orc.conv3(orc.lrelu(orc.instance_norm(r1)), w2, b2)
+    raw, st = ops.conv3d(dev(x), dev(w1), dev(b1), want_stats=True)
+    assert rel_err(raw.cpu(), r1) <= 2e-6
+    out, st2 = ops.conv3d(raw, dev(w2), dev(b2), in_stats=st, want_stats=True)
+    assert rel_err(out.cpu(), ref) <= 1e-5
+    st2 = st2.cpu().reshape(2, cout, 2)
+    assert torch.allclose(st2[..., 0], ref.double().sum(dim=(2, 3, 4)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st2[..., 1], (ref.double() ** 2).sum(dim=(2, 3, 4)), rtol=1e-4, atol=1e-2)
+
+
 @pytest.mark.parametrize("name", golden_names("cwm_"))
 def test_cwm_golden(name):
     from smilecode_b200 import models

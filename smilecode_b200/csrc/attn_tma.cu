@@ -514,10 +514,10 @@ fused_march_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
         if (z > nsteps) break;
         // storage roles of the three in-flight voxels: new (tap plane 0), middle (1), oldest (2: completes)
         const int sN = j, sM = (j + 2) % 3, sO = (j + 1) % 3;
-        if (((it ^ r) & 3) == 0) {  // two of the eight warps look per step; warps blocked on a late stage look as well
-          if (lane == 0) pseg = try_issue<TH, NS, COMPOSE>(sbase, segs, pseg, total_stages, &tm_k, &tm_q, &tm_f);
-          __syncwarp();
-        }
+        // every warp looks once per step, here and nowhere else: looking right after releasing a slot puts the work
+        // on the last arriver (measured 162 vs 155 us), looking with two warps of eight re-arms too late (161 us)
+        if (lane == 0) pseg = try_issue<TH, NS, COMPOSE>(sbase, segs, pseg, total_stages, &tm_k, &tm_q, &tm_f);
+        __syncwarp();
         float2 mv[4];            // moved-image corners as (z0, z1) pairs: y0x0, y0x1, y1x0, y1x1
         float mfx = 0.f, mfy = 0.f, mfz = 0.f;
         bool pend = false;
@@ -791,7 +791,6 @@ int launch_modet_attn_tma(const float* q, const float* k, const float* rpb, cons
   } while (0)
   static const int variant = [] { const char* e = getenv("SMILE_FUSED_VARIANT"); return e ? atoi(e) : 0; }();
   switch (variant) {  // tuning knob for profiling runs; 0 is the production configuration
-    case 1: SMILE_LAUNCH(4, 2);
     case 3: SMILE_LAUNCH(3, 3);
     case 9:  // per-warp barrier-wait timing printed from the kernel (profiling aid)
       if (compose && moved != nullptr)

@@ -213,6 +213,13 @@ int launch_conv3d(const float* in, const float* weight, const float* bias, float
                   double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
                   cudaStream_t st) {
   {
+    // layers wide enough for an MMA (>= 12 output channels) run on the tensor cores (conv_tc.cu); SMILE_CONV_TC=0
+    // keeps everything on the SIMT kernels
+    bool tc = false;
+    int rc = launch_conv3d_tc(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st, &tc);
+    if (tc) return rc;
+  }
+  {
     static const bool no_tma = getenv("SMILE_CONV_NO_TMA") != nullptr;  // profiling knob: force the generic kernel
     bool handled = false;
     if (!no_tma) {

@@ -28,6 +28,9 @@ int launch_proj_ln(const float* feat, const float* weight, const float* bias, co
 int launch_conv3d(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
                   double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
                   cudaStream_t st);
+int launch_conv3d_tc(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
+                     double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps, cudaStream_t st,
+                     bool* handled);
 int launch_conv3d_tma_flat(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
                            double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
                            cudaStream_t st, bool* handled);

@@ -82,8 +82,10 @@ __global__ void conv3d_tc_prep_kernel(const float* __restrict__ w, float* __rest
   wprep[e] = hl == 0 ? h : v - h;
 }
 
+constexpr int THREADS = 256;  // 8 warps: warps w and w + 4 share TMEM lane quadrant w and split the NT columns
+
 template <int NT, bool NORM>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(THREADS)
 conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, const float* __restrict__ bias,
                  float* __restrict__ out, const double* __restrict__ in_stats, double* __restrict__ out_stats, int Cin,
                  int Cout, int D, int H, int W, int tiles_plane, int nstage, int SEG, int act_out, float eps) {
@@ -96,8 +98,8 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
   uint8_t* tail = reinterpret_cast<uint8_t*>(sB) + B_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);    // [0] weights landed, [1] MMAs done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 16);
-  double* s_part = reinterpret_cast<double*>(tail + 32); // [128 / NT parts][NT][2]
-  float* s_mr = reinterpret_cast<float*>(tail + 32 + (128 / NT) * NT * 2 * 8);  // [nstage * 8][2] rstd, -mean*rstd
+  double* s_part = reinterpret_cast<double*>(tail + 32); // [THREADS / NT parts][NT][2]
+  float* s_mr = reinterpret_cast<float*>(tail + 32 + THREADS * 2 * 8);  // [nstage * 8][2] rstd, -mean*rstd
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Wp = W + 2, HW = H * W;
@@ -119,7 +121,7 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (NORM) {
-    for (int c = tid; c < nstage * KC; c += 128) {
+    for (int c = tid; c < nstage * KC; c += THREADS) {
       float rstd = 0.f, shift = 0.f;
       if (c < Cin) {
         const double s = in_stats[((long long)b * Cin + c) * 2], ss = in_stats[((long long)b * Cin + c) * 2 + 1];
@@ -137,9 +139,12 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  float acc[NT];
+  constexpr int NH = NT / 2;             // columns owned by this thread
+  const int row = (warp & 3) * 32 + lane;  // tile row (TMEM lane) of this thread
+  const int chalf = warp >> 2;             // which half of the NT columns
+  float acc[NH];
 #pragma unroll
-  for (int n = 0; n < NT; ++n) acc[n] = 0.f;
+  for (int n = 0; n < NH; ++n) acc[n] = 0.f;
 
   const float* inb = in + (long long)b * Cin * N;
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -155,13 +160,13 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
     }
     // ---- stage the activations: global NCDHW -> (normalise) -> hi/lo -> position-major float4
     const int ci0 = stage * KC;
-    for (int i0 = tid; i0 < items; i0 += 128 * 4) {
+    for (int i0 = tid; i0 < items; i0 += THREADS * 4) {
       float v[4][4];
       bool ok[4];
       int cbs[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * 128;
+        const int i = i0 + u * THREADS;
         const int s = i % SEG;
         const int t = i / SEG;
         const int cb = t & 1, kd = t >> 1;
@@ -179,7 +184,7 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * 128;
+        const int i = i0 + u * THREADS;
         if (i < items) {
           float hi[4], lo[4];
 #pragma unroll
@@ -235,10 +240,9 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-#pragma unroll
-      for (int c0 = 0; c0 < NT; c0 += 16) {
+      const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * NT + chalf * NH);
+      if (NH == 16) {
         uint32_t r[16];
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * NT + c0);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -246,7 +250,15 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+        for (int j = 0; j < 16; ++j) acc[j % NH] += __uint_as_float(r[j]);
+      } else {
+        uint32_t r[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j % NH] += __uint_as_float(r[j]);
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -256,31 +268,33 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
   // ---- epilogue: bias, store (+ optional LeakyReLU), InstanceNorm statistics of the raw output
   __syncthreads();  // every warp is done with TMEM and the operand buffers
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(G * NT));
-  const int q = q0 + tid;
+  const int q = q0 + row;
   int hp = (int)(((float)q + 0.5f) * inv_wp);
   if (hp * Wp > q) --hp;
   else if ((hp + 1) * Wp <= q) ++hp;
   const int wp = q - hp * Wp;
   const bool valid = q <= q_hi && wp >= 1 && wp <= W;  // rows are in range whenever q is
-  float* ob = out + ((long long)b * Cout + co0) * N + (long long)d * HW + (hp - 1) * W + (wp - 1);
+  const int cbase = co0 + chalf * NH;
+  float* ob = out + ((long long)b * Cout + cbase) * N + (long long)d * HW + (hp - 1) * W + (wp - 1);
   float* s_t = reinterpret_cast<float*>(smem);           // [NT][128] transposition buffer (operand buffer reused)
 #pragma unroll
-  for (int n = 0; n < NT; ++n) {
+  for (int n = 0; n < NH; ++n) {
     float val = 0.f;
-    if (valid && co0 + n < Cout) {
-      val = acc[n] + __ldg(bias + co0 + n);
+    if (valid && cbase + n < Cout) {
+      val = acc[n] + __ldg(bias + cbase + n);
       ob[(long long)n * N] = act_out ? lrelu01(val) : val;
     }
-    s_t[n * 128 + tid] = val;
+    s_t[(chalf * NH + n) * 128 + row] = val;
   }
   if (out_stats != nullptr) {
     __syncthreads();
-    constexpr int PARTS = 128 / NT;
+    constexpr int PARTS = THREADS / NT;   // each (channel, part) thread sums 128 / PARTS rows
+    constexpr int RP = 128 / PARTS;
     const int n = tid % NT, part = tid / NT;
     float ps = 0.f, pq = 0.f;
 #pragma unroll 8
-    for (int m = 0; m < NT; ++m) {
-      const float x = s_t[n * 128 + part * NT + ((m + tid) & (NT - 1))];  // rotated start: conflict-free
+    for (int m = 0; m < RP; ++m) {
+      const float x = s_t[n * 128 + part * RP + ((m + tid) & (RP - 1))];  // rotated start: conflict-free
       ps += x;
       pq = fmaf(x, x, pq);
     }
@@ -307,7 +321,7 @@ int launch_nt(const float* in, const float* weight, const float* bias, float* ou
   const int nstage = ceil_div(Cin, KC), ntiles_n = ceil_div(Cout, NT);
   const int tiles_plane = ceil_div((H - 1) * Wp + W, M);
   constexpr int B_BYTES = 2 * 27 * 2 * NT * 16;
-  const size_t smem = (size_t)2 * 3 * 2 * SEG * 16 + B_BYTES + 32 + (size_t)(128 / NT) * NT * 2 * 8 +
+  const size_t smem = (size_t)2 * 3 * 2 * SEG * 16 + B_BYTES + 32 + (size_t)THREADS * 2 * 8 +
                       (size_t)nstage * KC * 2 * 4 + 16;
   // weights, split and re-arranged for this launch (stream-ordered scratch)
   const long long welems = (long long)ntiles_n * nstage * (B_BYTES / 4);
@@ -325,7 +339,7 @@ int launch_nt(const float* in, const float* weight, const float* bias, float* ou
       set_error("conv3d(tcgen05): cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e2));
       return SMILE_ERR_CUDA;
     }
-    kern<<<grid, 128, smem, st>>>(in, wprep, bias, out, in_stats, out_stats, Cin, Cout, D, H, W, tiles_plane, nstage, SEG,
+    kern<<<grid, THREADS, smem, st>>>(in, wprep, bias, out, in_stats, out_stats, Cin, Cout, D, H, W, tiles_plane, nstage, SEG,
                                   act_out, eps);
     return check_launch("conv3d(tcgen05)");
   };
@@ -344,6 +358,9 @@ int launch_conv3d_tc(const float* in, const float* weight, const float* bias, fl
   *handled = false;
   static const int mode = [] { const char* e = getenv("SMILE_CONV_TC"); return e ? atoi(e) : 1; }();
   if (mode == 0 || Cout < 12 || H < 2 || W < 2) return SMILE_OK;
+  // measured on the B200 (this version stages every key plane three times and is bound by staging on wide volumes):
+  // ahead of the SIMT kernels from 16 input channels up on the coarse levels, behind them on the 80-wide level
+  if (mode == 1 && (Cin < 16 || W > 48)) return SMILE_OK;
   const int Wp = W + 2;
   const int SEG = M + 2 * (Wp + 1);
   const int NT = Cout <= 16 ? 16 : 32;

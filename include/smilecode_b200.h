@@ -188,6 +188,28 @@ int smile_grad3d_l2_bwd(const float* flow, float* d_flow, const float* gscale, i
 int smile_adam_amsgrad_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq,
                             long long n, float lr, float beta1, float beta2, float eps, int step, smile_stream_t stream);
 
+/* ---- evaluation path of ModeT/infer.py:86-92 -------------------------------------------------- */
+
+/* utils.register_model(img_size, 'nearest') (ModeT/utils.py:74-83 -> SpatialTransformer(mode='nearest'), 30-72):
+ * out[b,c,p] = src[b,c,nearbyint(p + flow[b,:,p])] with align_corners=True coordinates, 0 outside the volume.
+ * src/out [B,C,D,H,W], flow [B,3,D,H,W]. */
+int smile_warp3d_nearest_fwd(const float* src, const float* flow, float* out, int B, int C, int D, int H, int W,
+                             smile_stream_t stream);
+
+/* utils.dice_val_VOI (ModeT/utils.py:86-106) without the device->host copy of the volumes: for every label l of
+ * labels[0..nlabels) counts[3*i+0] = |pred==l & truth==l|, [3*i+1] = |pred==l|, [3*i+2] = |truth==l| (unsigned 64-bit,
+ * zeroed by the call).  pred/truth hold label values as fp32, compared after truncation (`.long()`, infer.py:91);
+ * labels must lie in [0, 1024), nlabels <= 256.  The caller forms mean_i 2*c0/(c1+c2+1e-5) in double. */
+int smile_dice_counts_fwd(const float* pred, const float* truth, const int* labels, int nlabels,
+                          unsigned long long* counts, long long n, smile_stream_t stream);
+
+/* utils.jacobian_determinant_vxm (ModeT/utils.py:108-150) for one 3-D displacement field flow[3,D,H,W]:
+ * np.gradient(disp + grid) in float64 (central differences, one-sided at the faces) and the 3x3 determinant,
+ * evaluated operation by operation like numpy.  det (optional, may be NULL): [D,H,W] float64; nonpos: number of
+ * voxels with det <= 0 (unsigned 64-bit, zeroed by the call) -- infer.py:90 divides it by D*H*W. */
+int smile_jacdet_fwd(const float* flow, double* det, unsigned long long* nonpos, int D, int H, int W,
+                     smile_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

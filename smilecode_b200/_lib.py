@@ -40,6 +40,9 @@ SIGNATURES = {
     "smile_ncc_vxm_bwd": [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     "smile_grad3d_l2_bwd": [P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     "smile_adam_amsgrad_step": [P, P, P, P, P, c_longlong, c_float, c_float, c_float, c_float, c_int, P],
+    "smile_warp3d_nearest_fwd": [P, P, P, c_int, c_int, c_int, c_int, c_int, P],
+    "smile_dice_counts_fwd": [P, P, P, c_int, P, c_longlong, P],
+    "smile_jacdet_fwd": [P, P, P, c_int, c_int, c_int, P],
 }
 
 _lib = None

@@ -360,4 +360,33 @@ int smile_adam_amsgrad_step(float* param, const float* grad, float* exp_avg, flo
                              (cudaStream_t)stream);
 }
 
+int smile_warp3d_nearest_fwd(const float* src, const float* flow, float* out, int B, int C, int D, int H, int W,
+                             smile_stream_t stream) {
+  REQUIRE_PTR(src);
+  REQUIRE_PTR(flow);
+  REQUIRE_PTR(out);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(C > 0, "%s: C=%d", __func__, C);
+  REQUIRE(out != src, "%s: out must not alias src", __func__);
+  return launch_warp3d_nearest(src, flow, out, B, C, D, H, W, (cudaStream_t)stream);
+}
+
+int smile_dice_counts_fwd(const float* pred, const float* truth, const int* labels, int nlabels,
+                          unsigned long long* counts, long long n, smile_stream_t stream) {
+  REQUIRE_PTR(pred);
+  REQUIRE_PTR(truth);
+  REQUIRE(labels != nullptr && counts != nullptr, "%s: labels / counts is NULL", __func__);
+  REQUIRE(nlabels > 0 && n > 0, "%s: nlabels=%d n=%lld", __func__, nlabels, n);
+  return launch_dice_counts(pred, truth, labels, nlabels, counts, n, (cudaStream_t)stream);
+}
+
+int smile_jacdet_fwd(const float* flow, double* det, unsigned long long* nonpos, int D, int H, int W,
+                     smile_stream_t stream) {
+  REQUIRE_PTR(flow);
+  REQUIRE(nonpos != nullptr, "%s: nonpos is NULL", __func__);
+  REQUIRE_VOL(1, D, H, W);
+  REQUIRE(D >= 2 && H >= 2 && W >= 2, "%s: np.gradient needs at least 2 samples per axis (D=%d H=%d W=%d)", __func__, D, H, W);
+  return launch_jacdet(flow, det, nonpos, D, H, W, (cudaStream_t)stream);
+}
+
 }  // extern "C"

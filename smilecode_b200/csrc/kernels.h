@@ -51,6 +51,13 @@ int launch_ncc_vxm(const float* y_true, const float* y_pred, float* out, float* 
 int launch_grad3d_l2(const float* flow, float* out, double* work, int B, int C, int D, int H, int W, cudaStream_t st);
 
 
+// metrics.cu (evaluation path of infer.py)
+int launch_warp3d_nearest(const float* src, const float* flow, float* out, int B, int C, int D, int H, int W,
+                          cudaStream_t st);
+int launch_dice_counts(const float* pred, const float* truth, const int* labels, int nlabels, unsigned long long* counts,
+                       long long n, cudaStream_t st);
+int launch_jacdet(const float* flow, double* det, unsigned long long* nonpos, int D, int H, int W, cudaStream_t st);
+
 // backward.cu (training path)
 int launch_warp3d_bwd(const float* g, const float* src, const float* flow, float* d_src, float* d_flow, int B, int C, int D,
                       int H, int W, cudaStream_t st);

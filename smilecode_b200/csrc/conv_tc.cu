@@ -18,6 +18,7 @@
 // summed in registers with round-to-nearest fp32 adds.
 #include <cstdint>
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -326,6 +327,22 @@ int launch_nt(const float* in, const float* weight, const float* bias, float* ou
   // weights, split and re-arranged for this launch (stream-ordered scratch)
   const long long welems = (long long)ntiles_n * nstage * (B_BYTES / 4);
   float* wprep = nullptr;
+  {
+    // The default memory pool hands unused memory back to the driver at every synchronisation (release threshold 0),
+    // which turns the next cudaMallocAsync into a multi-millisecond real allocation (measured: 18 ms per layer when
+    // the caller alternates streams).  Keep up to 64 MB of scratch cached in the pool instead.
+    static std::once_flag once[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::call_once(once[dev & 63], [dev] {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t cur = 0, want = 64ull << 20;
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur);
+        if (cur < want) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &want);
+      }
+    });
+  }
   cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&wprep), (size_t)welems * 4, st);
   if (e != cudaSuccess) {
     set_error("conv3d(tcgen05): cudaMallocAsync(%lld B) failed: %s", welems * 4, cudaGetErrorString(e));

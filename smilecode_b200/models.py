@@ -255,6 +255,10 @@ class ModeT(nn.Module):
     def forward(self, moving, fixed):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             return self._forward_train(moving, fixed)
+        with ops.stats_arena(moving.device):
+            return self._forward_infer(moving, fixed)
+
+    def _forward_infer(self, moving, fixed):
         B = moving.shape[0]
         feats = self.encoder(torch.cat([moving, fixed], 0))     # shared weights: one batched pass
         M = [f[:B] for f in feats]

@@ -37,6 +37,38 @@ def _chk(t: Tensor, name: str, ndim: int, dtype=torch.float32) -> Tensor:
     return t
 
 
+class stats_arena:
+    """One zero-filled fp64 buffer per forward pass that the InstanceNorm statistics of every conv3d are carved from
+    (one fill kernel instead of one per layer: sixteen 2-microsecond launches per ModeT forward).
+
+        with ops.stats_arena(device):
+            ... ops.conv3d(..., want_stats=True) ...
+    """
+    _active = None
+
+    def __init__(self, device, rows: int = 4096):
+        self.device, self.rows = device, rows
+
+    def __enter__(self):
+        self.buf = torch.zeros((self.rows, 2), device=self.device, dtype=torch.float64)
+        self.used = 0
+        self._prev, stats_arena._active = stats_arena._active, self
+        return self
+
+    def __exit__(self, *exc):
+        stats_arena._active = self._prev
+        return False
+
+    @staticmethod
+    def take(rows: int, device) -> Tensor:
+        a = stats_arena._active
+        if a is None or a.buf.device != device or a.used + rows > a.rows:
+            return torch.zeros((rows, 2), device=device, dtype=torch.float64)
+        out = a.buf[a.used:a.used + rows]
+        a.used += rows
+        return out
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -184,7 +216,7 @@ def conv3d(x: Tensor, weight: Tensor, bias: Tensor, in_stats: Optional[Tensor] =
         if tuple(in_stats.shape) != (B * Cin, 2):
             raise SmileError("in_stats must be [B*Cin, 2] float64")
     out = torch.empty((B, Cout, D, H, W), device=x.device, dtype=torch.float32)
-    stats = torch.zeros((B * Cout, 2), device=x.device, dtype=torch.float64) if want_stats else None
+    stats = stats_arena.take(B * Cout, x.device) if want_stats else None
     call("smile_conv3d_fwd", x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), _ptr(in_stats), _ptr(stats),
          B, Cin, Cout, D, H, W, int(act_out), float(eps), _stream(), label=f"[{Cin}->{Cout} {D}x{H}x{W}]")
     return out, stats

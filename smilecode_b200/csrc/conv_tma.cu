@@ -59,6 +59,7 @@ int launch_conv3d_tma(const float* in, const float* weight, const float* bias, f
     }
   }
   if (TWL == 32) {
+    if (CO == 4 && V == 8 && Cin == 1) SMILE_TCONV(4, 8, 32, 8, 1);  // first layer: do not stage / multiply a phantom channel
     if (CO == 4 && V == 8) SMILE_TCONV(4, 8, 32, 8, 2);
     if (CO == 4 && V == 4) SMILE_TCONV(4, 4, 32, 8, 4);
     if (CO == 4) SMILE_TCONV(4, 2, 32, 8, 4);

@@ -31,10 +31,10 @@ constexpr int TW = 32;        // voxels per tile row (one per lane)
 // boxes start a little further left than the 1-voxel halo: 2 voxels (48 B) for keys, 4 floats for flow.
 constexpr int KW = TW + 4;    // key row: voxels w0-2 .. w0+33
 constexpr int KOFF = 1;       // tile column of voxel (w - 1) for lane 0
-// Flow rows are staged 64 floats wide although only w0-4 .. w0+35 is used: with a row pitch (and plane pitch) that
-// is a multiple of 32 banks, the bank of a compose-gather depends on the lane alone, not on which of the rows /
-// planes the lane picked, so the per-lane corner choice no longer causes ~2.6-way conflicts.
-constexpr int FWP = 64;
+// Flow row pitch: 40 floats (w0-4 .. w0+35) are needed.  Wider pitches change the bank pattern of the compose gather
+// (with 64 the bank depends on the lane only); measured on the B200 at 160x192x160: 40 -> 155.1 us, 48 -> 153.8 us,
+// 64 -> 155 us, i.e. no effect beyond noise -- the gather conflicts are not what limits the kernel.  48 is kept.
+constexpr int FWP = 48;
 constexpr int FOFF = 3;       // tile column of voxel (w - 1) for lane 0
 constexpr int HD = 6;         // head_dim of the reference configuration
 constexpr float kLog2e = 1.4426950408889634f;
@@ -791,7 +791,8 @@ int launch_modet_attn_tma(const float* q, const float* k, const float* rpb, cons
   } while (0)
   static const int variant = [] { const char* e = getenv("SMILE_FUSED_VARIANT"); return e ? atoi(e) : 0; }();
   switch (variant) {  // tuning knob for profiling runs; 0 is the production configuration
-    case 3: SMILE_LAUNCH(3, 3);
+    case 1: SMILE_LAUNCH(4, 2);  // 4-deep ring: 159.7 us vs 155 us (measured)
+    case 3: SMILE_LAUNCH(3, 3);  // 3 CTAs/SM at 80 registers: spills, 200 us (measured)
     case 9:  // per-warp barrier-wait timing printed from the kernel (profiling aid)
       if (compose && moved != nullptr)
         return launch_cfg<TH, 3, true, true, 2, true>(mk, mq, mf, rpb, flow_in, moving, flow_out, moved, dm, grid, qscale, post,

@@ -13,9 +13,10 @@
 //     pre-arranged block (conv3d_tc_prep_kernel).
 // Accuracy (tools/probe/tf32x3_probe.cu): a tf32 MMA keeps 11 significant bits per operand and the TMEM
 // accumulation error grows with the number of accumulated MMAs.  So (i) every operand is split x = hi + lo
-// (hi = x with the low 13 mantissa bits cleared) and each tap issues hi*hi + lo*hi + hi*lo, and (ii) the 27 taps of a
-// stage accumulate into EIGHT separate TMEM accumulators (<= 12 MMAs each) that are drained after every stage and
-// summed in registers with round-to-nearest fp32 adds.
+// (hi = x with the low 13 mantissa bits cleared) and each tap computes hi*hi + lo*hi + hi*lo, and (ii) the 27 taps of a
+// stage accumulate into FOUR groups of TMEM accumulators (<= 14 MMAs each) that are drained after every stage and
+// summed in registers with round-to-nearest fp32 adds.  hi*hi and hi*lo share one MMA (B operand [B_hi | B_lo], N = 2*NT),
+// so a tap costs two MMAs and the A_hi tile is read from shared memory once instead of twice.
 #include <cstdint>
 #include <cstdlib>
 #include <mutex>
@@ -28,8 +29,8 @@ namespace {
 
 constexpr int M = 128;        // positions per tile (UMMA M)
 constexpr int KC = 8;         // input channels per stage (UMMA K for tf32)
-constexpr int G = 8;          // TMEM accumulators per tile
-__device__ __constant__ int kGroupStart[G + 1] = {0, 4, 8, 12, 15, 18, 21, 24, 27};
+constexpr int G = 4;          // TMEM accumulator groups per tile (each 2*NT columns: [hi*hi + lo*hi | hi*lo])
+__device__ __constant__ int kGroupStart[G + 1] = {0, 7, 14, 21, 27};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -62,8 +63,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-// weight [Cout][Cin][27]  ->  wprep[ntile][stage][hi/lo][tap][cb(2)][NT][4]; channel ci = stage*8 + cb*4 + j,
-// output channel co = ntile*NT + n; zero outside the tensor
+// weight [Cout][Cin][27]  ->  wprep[ntile][stage][tap][cb(2)][hi/lo][NT][4]; channel ci = stage*8 + cb*4 + j,
+// output channel co = ntile*NT + n; zero outside the tensor.  Per (tap, cb) the NT hi rows are followed by the NT lo
+// rows, so one B descriptor with N = 2*NT covers [B_hi | B_lo] and one with N = NT covers B_hi alone.
 __global__ void conv3d_tc_prep_kernel(const float* __restrict__ w, float* __restrict__ wprep, int Cout, int Cin, int NT,
                                       int nstage, long long total) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -71,9 +73,9 @@ __global__ void conv3d_tc_prep_kernel(const float* __restrict__ w, float* __rest
   long long t = e;
   const int j = (int)(t % 4); t /= 4;
   const int n = (int)(t % NT); t /= NT;
+  const int hl = (int)(t % 2); t /= 2;
   const int cb = (int)(t % 2); t /= 2;
   const int tap = (int)(t % 27); t /= 27;
-  const int hl = (int)(t % 2); t /= 2;
   const int stage = (int)(t % nstage); t /= nstage;
   const int ntile = (int)t;
   const int ci = stage * KC + cb * 4 + j, co = ntile * NT + n;
@@ -94,7 +96,7 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
   // [hi/lo][3 planes][2 channel blocks][SEG positions][4 channels]
   float4* sA = reinterpret_cast<float4*>(smem);
   const int a_plane = 3 * 2 * SEG;                       // float4 elements of one hi or lo copy
-  float* sB = reinterpret_cast<float*>(smem + (size_t)2 * a_plane * 16);   // [hi/lo][27][2][NT][4]
+  float* sB = reinterpret_cast<float*>(smem + (size_t)2 * a_plane * 16);   // [27][2][hi/lo][NT][4]
   constexpr int B_BYTES = 2 * 27 * 2 * NT * 16;
   uint8_t* tail = reinterpret_cast<uint8_t*>(sB) + B_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);    // [0] weights landed, [1] MMAs done
@@ -118,7 +120,7 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(G * NT));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(G * 2 * NT));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (NORM) {
@@ -148,7 +150,8 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
   for (int n = 0; n < NH; ++n) acc[n] = 0.f;
 
   const float* inb = in + (long long)b * Cin * N;
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(M >> 4) << 24);
+  const uint32_t idesc_n = idesc_base | ((uint32_t)(NT >> 3) << 17), idesc_2n = idesc_base | ((uint32_t)(2 * NT >> 3) << 17);
   const int items = 3 * 2 * SEG;  // float4 items per stage
   const int s_base = q0 - (Wp + 1);  // padded index of staged position 0
 
@@ -212,24 +215,24 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
     if (tid == 0) {
       mbar_wait(smem_u32(bars), ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + (uint32_t)a_plane * 16, b_hi = smem_u32(sB),
-                     b_lo = b_hi + 27 * 2 * NT * 16;
+      const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + (uint32_t)a_plane * 16, b_base = smem_u32(sB);
       int g = 0;
       for (int tap = 0; tap < 27; ++tap) {
         if (tap >= kGroupStart[g + 1]) ++g;
         const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
         const uint32_t a_off = (uint32_t)((kd * 2 * SEG + (Wp + 1) + (kh - 1) * Wp + (kw - 1)) * 16);
-        const uint32_t b_off = (uint32_t)(tap * 2 * NT * 16);
-        const uint32_t dcol = tmem + (uint32_t)(g * NT);
+        const uint32_t b_off = (uint32_t)(tap * 2 * 2 * NT * 16);   // [tap][cb][hi/lo][NT][4]: cb stride = 2*NT*16
+        const uint32_t dcol = tmem + (uint32_t)(g * 2 * NT);
+        // A_hi x [B_hi | B_lo]  (N = 2*NT: hi*hi into columns [0,NT), hi*lo into [NT,2NT)), then A_lo x B_hi into [0,NT)
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
+        for (int pass = 0; pass < 2; ++pass) {
           const uint64_t da = make_desc((pass == 1 ? a_lo : a_hi) + a_off, (uint32_t)SEG * 16, 128);
-          const uint64_t db = make_desc((pass == 2 ? b_lo : b_hi) + b_off, NT * 16, 128);
+          const uint64_t db = make_desc(b_base + b_off, 2 * NT * 16, 128);
           const uint32_t accum = (tap > kGroupStart[g] || pass > 0) ? 1u : 0u;
           asm volatile(
               "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-              ::"r"(dcol), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+              ::"r"(dcol), "l"(da), "l"(db), "r"(pass == 0 ? idesc_2n : idesc_n), "r"(accum)
               : "memory");
         }
       }
@@ -240,8 +243,8 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
     mbar_wait(smem_u32(bars + 1), ph);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * NT + chalf * NH);
+    for (int gb = 0; gb < 2 * G; ++gb) {   // per group: the [hi*hi + lo*hi] block, then the [hi*lo] block
+      const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(gb * NT + chalf * NH);
       if (NH == 16) {
         uint32_t r[16];
         asm volatile(
@@ -268,7 +271,7 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
 
   // ---- epilogue: bias, store (+ optional LeakyReLU), InstanceNorm statistics of the raw output
   __syncthreads();  // every warp is done with TMEM and the operand buffers
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(G * NT));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(G * 2 * NT));
   const int q = q0 + row;
   int hp = (int)(((float)q + 0.5f) * inv_wp);
   if (hp * Wp > q) --hp;

@@ -73,7 +73,12 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.03)
+
+    def reset(self):
+        """Forget what was sampled so far (the sampler is started during warm-up: the first NVML queries of a fresh
+        process take tens of milliseconds and contend with kernel launches, which must not fall into the timed region)."""
+        self.samples, self.reasons = [], set()
 
     def __enter__(self):
         if self.nv is not None:
@@ -198,6 +203,8 @@ def main():
             return float(t.item())
         return x
 
+    clk = ClockSampler(physical_device_index(local))
+    clk.__enter__()                      # sampling starts with the warm-up, its samples are dropped below
     with torch.no_grad():
         for _ in range(W):
             y, flow = model(moving, fixed)
@@ -207,13 +214,14 @@ def main():
         l0 = _lib.LAUNCHES
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         barrier()
-        with ClockSampler(physical_device_index(local)) as clk:
-            for a, b in evs:
-                flush.zero_()
-                a.record(stream)
-                y, flow = model(moving, fixed)
-                b.record(stream)
-            barrier()
+        clk.reset()
+        for a, b in evs:
+            flush.zero_()
+            a.record(stream)
+            y, flow = model(moving, fixed)
+            b.record(stream)
+        barrier()
+        clk.__exit__()
         launches = _lib.LAUNCHES - l0
         total_ms = reduce_max(sum(a.elapsed_time(b) for a, b in evs))
         value = world * K / (total_ms * 1e-3)

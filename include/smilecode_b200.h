@@ -92,6 +92,17 @@ int smile_conv3d_fwd(const float* in, const float* weight, const float* bias, fl
                      double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
                      smile_stream_t stream);
 
+/* Optional prepared weights for the tensor-core convolution (layers with >= 16 input and >= 12 output channels on
+ * volumes up to 48 voxels wide run on tcgen05 with a 3xTF32 split, csrc/conv_tc.cu).  smile_conv3d_fwd prepares the
+ * split weights on every call into stream-ordered scratch; a caller with constant weights can do it once:
+ *   n = smile_conv3d_tc_prep_floats(Cin, Cout);  allocate n floats;  smile_conv3d_tc_prep(weight, wprep, Cin, Cout, s);
+ *   smile_conv3d_prepped_fwd(..., wprep, ...)   -- same contract as smile_conv3d_fwd; wprep may be NULL. */
+long long smile_conv3d_tc_prep_floats(int Cin, int Cout);
+int smile_conv3d_tc_prep(const float* weight, float* wprep, int Cin, int Cout, smile_stream_t stream);
+int smile_conv3d_prepped_fwd(const float* in, const float* weight, const float* wprep, const float* bias, float* out,
+                             const double* in_stats, double* out_stats, int B, int Cin, int Cout, int D, int H, int W,
+                             int act_out, float eps, smile_stream_t stream);
+
 /* a8  InstanceNorm3d + LeakyReLU(0.1) from fp64 sums (models.py:149-150), and AvgPool3d(2)
  * (models.py:198) of the result into `pooled` [B,C,D/2,H/2,W/2] when pooled != NULL.  out may alias raw. */
 int smile_instnorm_lrelu_pool_fwd(const float* raw, const double* stats, float* out, float* pooled, int B, int C, int D,

@@ -40,6 +40,8 @@ SIGNATURES = {
     "smile_ncc_vxm_bwd": [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     "smile_grad3d_l2_bwd": [P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     "smile_adam_amsgrad_step": [P, P, P, P, P, c_longlong, c_float, c_float, c_float, c_float, c_int, P],
+    "smile_conv3d_tc_prep": [P, P, c_int, c_int, P],
+    "smile_conv3d_prepped_fwd": [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P],
     "smile_warp3d_nearest_fwd": [P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     "smile_dice_counts_fwd": [P, P, P, c_int, P, c_longlong, P],
     "smile_jacdet_fwd": [P, P, P, c_int, c_int, c_int, P],
@@ -66,6 +68,8 @@ def lib() -> ctypes.CDLL:
         handle.smile_last_error.argtypes = []
         handle.smile_ncc_vxm_work_bytes.restype = c_longlong
         handle.smile_ncc_vxm_work_bytes.argtypes = [c_int, c_int, c_int, c_int]
+        handle.smile_conv3d_tc_prep_floats.restype = c_longlong
+        handle.smile_conv3d_tc_prep_floats.argtypes = [c_int, c_int]
         for name, argtypes in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype = c_int

@@ -159,6 +159,34 @@ int smile_conv3d_fwd(const float* in, const float* weight, const float* bias, fl
                        (cudaStream_t)stream);
 }
 
+long long smile_conv3d_tc_prep_floats(int Cin, int Cout) {
+  if (Cin <= 0 || Cout <= 0 || Cin > 4096 || Cout > 4096) return 0;
+  return conv3d_tc_prep_floats(Cin, Cout);
+}
+
+int smile_conv3d_tc_prep(const float* weight, float* wprep, int Cin, int Cout, smile_stream_t stream) {
+  REQUIRE_PTR(weight);
+  REQUIRE_PTR(wprep);
+  REQUIRE(Cin > 0 && Cout > 0 && Cin <= 4096 && Cout <= 4096, "%s: Cin=%d Cout=%d out of range", __func__, Cin, Cout);
+  return launch_conv3d_tc_prep(weight, wprep, Cin, Cout, (cudaStream_t)stream);
+}
+
+int smile_conv3d_prepped_fwd(const float* in, const float* weight, const float* wprep, const float* bias, float* out,
+                             const double* in_stats, double* out_stats, int B, int Cin, int Cout, int D, int H, int W,
+                             int act_out, float eps, smile_stream_t stream) {
+  REQUIRE_PTR(in);
+  REQUIRE_PTR(weight);
+  REQUIRE_PTR(bias);
+  REQUIRE_PTR(out);
+  REQUIRE(wprep == nullptr || aligned16(wprep), "%s: wprep not 16-byte aligned", __func__);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(Cin > 0 && Cout > 0 && Cin <= 4096 && Cout <= 4096, "%s: Cin=%d Cout=%d out of range", __func__, Cin, Cout);
+  REQUIRE(in != out, "%s: out must not alias in", __func__);
+  REQUIRE((long long)B <= 65535, "%s: B=%d exceeds grid.z", __func__, B);
+  return launch_conv3d(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps,
+                       (cudaStream_t)stream, wprep);
+}
+
 int smile_instnorm_lrelu_pool_fwd(const float* raw, const double* stats, float* out, float* pooled, int B, int C, int D,
                                   int H, int W, float eps, smile_stream_t stream) {
   REQUIRE_PTR(raw);

@@ -211,12 +211,12 @@ int launch_conv3d_small(const float* in, const float* weight, const float* bias,
 
 int launch_conv3d(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
                   double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
-                  cudaStream_t st) {
+                  cudaStream_t st, const float* wprep) {
   {
     // layers wide enough for an MMA (>= 12 output channels) run on the tensor cores (conv_tc.cu); SMILE_CONV_TC=0
     // keeps everything on the SIMT kernels
     bool tc = false;
-    int rc = launch_conv3d_tc(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st, &tc);
+    int rc = launch_conv3d_tc(in, weight, wprep, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st, &tc);
     if (tc) return rc;
   }
   {

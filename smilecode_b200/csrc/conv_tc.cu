@@ -318,8 +318,9 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
 }
 
 template <int NT>
-int launch_nt(const float* in, const float* weight, const float* bias, float* out, const double* in_stats, double* out_stats,
-              int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps, cudaStream_t st) {
+int launch_nt(const float* in, const float* weight, const float* wprep_in, const float* bias, float* out,
+              const double* in_stats, double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
+              cudaStream_t st) {
   const int Wp = W + 2;
   const int SEG = M + 2 * (Wp + 1);
   const int nstage = ceil_div(Cin, KC), ntiles_n = ceil_div(Cout, NT);
@@ -327,10 +328,12 @@ int launch_nt(const float* in, const float* weight, const float* bias, float* ou
   constexpr int B_BYTES = 2 * 27 * 2 * NT * 16;
   const size_t smem = (size_t)2 * 3 * 2 * SEG * 16 + B_BYTES + 32 + (size_t)THREADS * 2 * 8 +
                       (size_t)nstage * KC * 2 * 4 + 16;
-  // weights, split and re-arranged for this launch (stream-ordered scratch)
+  // weights split and re-arranged: prepared once by the caller (smile_conv3d_tc_prep), or per launch into
+  // stream-ordered scratch
   const long long welems = (long long)ntiles_n * nstage * (B_BYTES / 4);
-  float* wprep = nullptr;
-  {
+  float* scratch = nullptr;
+  const float* wprep = wprep_in;
+  if (wprep == nullptr) {
     // The default memory pool hands unused memory back to the driver at every synchronisation (release threshold 0),
     // which turns the next cudaMallocAsync into a multi-millisecond real allocation (measured: 18 ms per layer when
     // the caller alternates streams).  Keep up to 64 MB of scratch cached in the pool instead.
@@ -345,13 +348,14 @@ int launch_nt(const float* in, const float* weight, const float* bias, float* ou
         if (cur < want) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &want);
       }
     });
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&scratch), (size_t)welems * 4, st);
+    if (e != cudaSuccess) {
+      set_error("conv3d(tcgen05): cudaMallocAsync(%lld B) failed: %s", welems * 4, cudaGetErrorString(e));
+      return SMILE_ERR_CUDA;
+    }
+    conv3d_tc_prep_kernel<<<(unsigned)ceil_div_ll(welems, 256), 256, 0, st>>>(weight, scratch, Cout, Cin, NT, nstage, welems);
+    wprep = scratch;
   }
-  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&wprep), (size_t)welems * 4, st);
-  if (e != cudaSuccess) {
-    set_error("conv3d(tcgen05): cudaMallocAsync(%lld B) failed: %s", welems * 4, cudaGetErrorString(e));
-    return SMILE_ERR_CUDA;
-  }
-  conv3d_tc_prep_kernel<<<(unsigned)ceil_div_ll(welems, 256), 256, 0, st>>>(weight, wprep, Cout, Cin, NT, nstage, welems);
   dim3 grid(tiles_plane * D, ntiles_n, B);
   auto run = [&](auto kern) {
     cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -364,17 +368,33 @@ int launch_nt(const float* in, const float* weight, const float* bias, float* ou
     return check_launch("conv3d(tcgen05)");
   };
   const int rc = (in_stats != nullptr) ? run(conv3d_tc_kernel<NT, true>) : run(conv3d_tc_kernel<NT, false>);
-  cudaFreeAsync(wprep, st);
+  if (scratch != nullptr) cudaFreeAsync(scratch, st);
   return rc;
 }
 
 }  // namespace
 
+// Prepared-weight interface: NT is a function of Cout only, so a caller can prepare once per weight tensor.
+static int tc_nt(int Cout) { return Cout <= 16 ? 16 : 32; }
+
+long long conv3d_tc_prep_floats(int Cin, int Cout) {
+  const int NT = tc_nt(Cout);
+  return (long long)ceil_div(Cout, NT) * ceil_div(Cin, KC) * (2 * 27 * 2 * NT * 4);
+}
+
+int launch_conv3d_tc_prep(const float* weight, float* wprep, int Cin, int Cout, cudaStream_t st) {
+  const int NT = tc_nt(Cout);
+  const long long welems = conv3d_tc_prep_floats(Cin, Cout);
+  conv3d_tc_prep_kernel<<<(unsigned)ceil_div_ll(welems, 256), 256, 0, st>>>(weight, wprep, Cout, Cin, NT, ceil_div(Cin, KC),
+                                                                            welems);
+  return check_launch("conv3d_tc_prep");
+}
+
 // Tensor-core path for layers with enough output channels to fill an MMA (N >= 16 after padding).  *handled = false
-// leaves the layer to the SIMT kernels.
-int launch_conv3d_tc(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
-                     double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
-                     cudaStream_t st, bool* handled) {
+// leaves the layer to the SIMT kernels.  wprep: weights prepared by launch_conv3d_tc_prep, or NULL.
+int launch_conv3d_tc(const float* in, const float* weight, const float* wprep, const float* bias, float* out,
+                     const double* in_stats, double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out,
+                     float eps, cudaStream_t st, bool* handled) {
   *handled = false;
   static const int mode = [] { const char* e = getenv("SMILE_CONV_TC"); return e ? atoi(e) : 1; }();
   if (mode == 0 || Cout < 12 || H < 2 || W < 2) return SMILE_OK;
@@ -383,12 +403,13 @@ int launch_conv3d_tc(const float* in, const float* weight, const float* bias, fl
   if (mode == 1 && (Cin < 16 || W > 48)) return SMILE_OK;
   const int Wp = W + 2;
   const int SEG = M + 2 * (Wp + 1);
-  const int NT = Cout <= 16 ? 16 : 32;
+  const int NT = tc_nt(Cout);
   const size_t smem = (size_t)2 * 3 * 2 * SEG * 16 + 2 * 27 * 2 * NT * 16 + 4096;
   if (smem > 200 * 1024 || (long long)(H + 2) * Wp >= (1 << 22)) return SMILE_OK;  // very wide rows: SIMT path
   *handled = true;
-  if (NT == 16) return launch_nt<16>(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st);
-  return launch_nt<32>(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st);
+  if (NT == 16)
+    return launch_nt<16>(in, weight, wprep, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st);
+  return launch_nt<32>(in, weight, wprep, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st);
 }
 
 }  // namespace smile

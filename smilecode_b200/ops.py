@@ -199,12 +199,38 @@ def warp_proj_ln(src: Tensor, flow: Tensor, weight: Tensor, bias: Tensor, gamma:
     return out
 
 
+# Split / re-arranged weights for the tensor-core convolution, prepared once per nn.Parameter and refreshed when the
+# parameter is updated in place (optimizer step -> version counter) or re-allocated.  Plain tensors (e.g. the flipped
+# weights of the data-gradient pass) are not cached: the library prepares them per call.
+_WPREP_CACHE: dict = {}
+
+
+def _prepared_weights(weight: Tensor, Cin: int, Cout: int) -> Optional[Tensor]:
+    # inference only: a training step rewrites the parameters through raw pointers (fused Adam over the flat buffer),
+    # which torch's version counter does not see
+    if torch.is_grad_enabled() or not isinstance(weight, torch.nn.Parameter) or Cin < 16 or Cout < 12:
+        return None
+    key = id(weight)
+    hit = _WPREP_CACHE.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
+        return hit[3]
+    import weakref
+    from ._lib import lib
+    n = int(lib().smile_conv3d_tc_prep_floats(Cin, Cout))
+    wprep = torch.empty(n, device=weight.device, dtype=torch.float32)
+    call("smile_conv3d_tc_prep", weight.data_ptr(), wprep.data_ptr(), Cin, Cout, _stream())
+    _WPREP_CACHE[key] = (weakref.ref(weight, lambda _r, k=key: _WPREP_CACHE.pop(k, None)), weight._version,
+                         weight.data_ptr(), wprep)
+    return wprep
+
+
 def conv3d(x: Tensor, weight: Tensor, bias: Tensor, in_stats: Optional[Tensor] = None, want_stats: bool = False,
            act_out: bool = False, eps: float = IN_EPS) -> Tuple[Tensor, Optional[Tensor]]:
     """Conv3d(k=3, s=1, p=1) (ModeT/models.py:127, 143, 253).  With `in_stats` the input is a raw conv
     output whose InstanceNorm+LeakyReLU is applied on load; with `want_stats` the fp64 (sum, sumsq)
     of the raw output per (b, c) are returned for the next InstanceNorm."""
     x = _chk(x, "x", 5)
+    weight_in = weight
     weight = _chk(weight, "weight", 5)
     bias = _chk(bias, "bias", 1)
     B, Cin, D, H, W = x.shape
@@ -217,8 +243,15 @@ def conv3d(x: Tensor, weight: Tensor, bias: Tensor, in_stats: Optional[Tensor] =
             raise SmileError("in_stats must be [B*Cin, 2] float64")
     out = torch.empty((B, Cout, D, H, W), device=x.device, dtype=torch.float32)
     stats = stats_arena.take(B * Cout, x.device) if want_stats else None
-    call("smile_conv3d_fwd", x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), _ptr(in_stats), _ptr(stats),
-         B, Cin, Cout, D, H, W, int(act_out), float(eps), _stream(), label=f"[{Cin}->{Cout} {D}x{H}x{W}]")
+    wprep = _prepared_weights(weight_in, Cin, Cout) if weight is weight_in else None
+    if wprep is not None:
+        call("smile_conv3d_prepped_fwd", x.data_ptr(), weight.data_ptr(), wprep.data_ptr(), bias.data_ptr(), out.data_ptr(),
+             _ptr(in_stats), _ptr(stats), B, Cin, Cout, D, H, W, int(act_out), float(eps), _stream(),
+             label=f"[{Cin}->{Cout} {D}x{H}x{W}]")
+        # the breakdown tools key on the smile_conv3d_fwd label
+    else:
+        call("smile_conv3d_fwd", x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), _ptr(in_stats),
+             _ptr(stats), B, Cin, Cout, D, H, W, int(act_out), float(eps), _stream(), label=f"[{Cin}->{Cout} {D}x{H}x{W}]")
     return out, stats
 
 
@@ -433,6 +466,7 @@ def grad3d_l2_bwd(flow: Tensor, gscale: Optional[Tensor]) -> Tensor:
 def adam_amsgrad_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, max_exp_avg_sq: Tensor, lr: float,
                       beta1: float, beta2: float, eps: float, step: int) -> None:
     """In-place torch.optim.Adam(amsgrad=True) update of a flat fp32 buffer."""
+    _WPREP_CACHE.clear()   # the parameters change behind torch's version counters
     for t in (param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq):
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise SmileError("adam_amsgrad_step: all buffers must be contiguous fp32 CUDA tensors")

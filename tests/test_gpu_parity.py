@@ -173,6 +173,24 @@ def test_conv_flat_tiles_norm_on_load(ops, cin, cout, shape):
     assert torch.allclose(st2[..., 1], (ref.double() ** 2).sum(dim=(2, 3, 4)), rtol=1e-4, atol=1e-2)
 
 
+def test_conv_prepared_weight_cache(ops):
+    """Tensor-core conv with weights prepared once per nn.Parameter (inference): same result as the per-call path,
+    and the cache follows in-place updates of the parameter."""
+    g = torch.Generator().manual_seed(12)
+    x = dev(torch.randn(1, 32, 6, 9, 12, generator=g))
+    w = torch.nn.Parameter(dev(torch.randn(32, 32, 3, 3, 3, generator=g) / (27 * 32) ** 0.5))
+    b = dev(torch.randn(32, generator=g) * 0.1)
+    with torch.no_grad():
+        plain, _ = ops.conv3d(x, w.detach().clone(), b)          # plain tensor: prepared inside the library per call
+        cached1, _ = ops.conv3d(x, w, b)                          # nn.Parameter: prepared once, cached
+        cached2, _ = ops.conv3d(x, w, b)
+        assert torch.equal(plain, cached1) and torch.equal(cached1, cached2)
+        assert rel_err(plain.cpu(), orc.conv3(x.cpu(), w.detach().cpu(), b.cpu())) <= 2e-6
+        w.mul_(-2.0)                                              # in-place update bumps the version counter
+        upd, _ = ops.conv3d(x, w, b)
+        assert rel_err(upd.cpu(), orc.conv3(x.cpu(), w.detach().cpu(), b.cpu())) <= 2e-6
+
+
 @pytest.mark.parametrize("name", golden_names("cwm_"))
 def test_cwm_golden(name):
     from smilecode_b200 import models

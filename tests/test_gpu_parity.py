@@ -269,6 +269,27 @@ def test_end_to_end_golden(name):
     assert (moved.cpu() - g["moved"]).abs().max() <= 1e-4
 
 
+def test_end_to_end_batch_matches_single_samples():
+    """Volume pairs are independent (InstanceNorm / LayerNorm are per sample): a batch of two pairs gives each pair the
+    flow it gets alone (up to the order of the fp64 statistics atomics)."""
+    from smilecode_b200 import models
+    from smilecode_b200.synth import make_pair
+    shape, heads = (32, 48, 32), [8, 4, 2, 1, 1]
+    sd = orc.synth_state_dict(seed=1234, num_heads=heads)
+    model = models.ModeT(shape, head_dim=6, num_heads=heads, scale=1)
+    model.load_state_dict(sd, strict=False)
+    model = model.cuda().eval()
+    m0, f0 = make_pair(shape, batch=1, seed=24)
+    m1, f1 = make_pair(shape, batch=1, seed=77)
+    with torch.no_grad():
+        y_b, flow_b = model(dev(torch.cat([m0, m1])), dev(torch.cat([f0, f1])))
+        y_0, flow_0 = model(dev(m0), dev(f0))
+        y_1, flow_1 = model(dev(m1), dev(f1))
+    assert (flow_b[0:1] - flow_0).abs().max() <= 2e-5 and (flow_b[1:2] - flow_1).abs().max() <= 2e-5
+    assert (y_b[0:1] - y_0).abs().max() <= 2e-5 and (y_b[1:2] - y_1).abs().max() <= 2e-5
+    assert (flow_0 - flow_1).abs().max() > 1e-2          # the two pairs are really different
+
+
 def test_errors_are_loud(ops):
     with pytest.raises(Exception):
         ops.warp3d(torch.zeros(1, 1, 4, 4, 4), torch.zeros(1, 3, 4, 4, 4))        # CPU tensors: no fallback

@@ -279,6 +279,23 @@ def main():
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": FUSED_L1_BYTES_PER_VOXEL * N1,
                     "launch_ms": k_ms}
 
+        # ---------------- informational: the same forward with four pairs per launch (the coarse levels fill the GPU better)
+        batched = None
+        if rank == 0 and world == 1:
+            mb, fb = moving.repeat(4, 1, 1, 1, 1), fixed.repeat(4, 1, 1, 1, 1)
+            for _ in range(2):
+                model(mb, fb)
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record(stream)
+            for _ in range(5):
+                model(mb, fb)
+            b1.record(stream)
+            torch.cuda.synchronize()
+            bms = b0.elapsed_time(b1) / 5
+            batched = {"pairs_per_launch": 4, "value": 4e3 / bms, "unit": UNIT, "ms_per_launch": bms,
+                       "note": "not the headline: BASELINE configs[1] is one pair per forward"}
+            del mb, fb
+
         breakdown = None
         if args.breakdown or rank == 0:
             _lib.profile_start()
@@ -348,7 +365,7 @@ def main():
                 "dtype": "f32", "data": "synthetic", "config": workload_config(1, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / K},
-                "gpu_launches": launches, "gpu_launches_per_step": launches // K, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "train": train}
+                "gpu_launches": launches, "gpu_launches_per_step": launches // K, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "train": train, "batched": batched}
         if breakdown:
             line["kernel_ms"] = {name: round(ms, 4) for ms, _, name in breakdown[:12]}
         print(json.dumps(line))

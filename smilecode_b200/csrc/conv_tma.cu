@@ -1,4 +1,5 @@
 // Conv3d 3x3x3 / pad 1, fp32 SIMT with TMA-staged input tiles: shape dispatch (kernel in conv_tma.cuh).
+#include <cstdio>
 #include <cstdlib>
 
 #include "conv_tma.cuh"
@@ -16,7 +17,7 @@ int launch_conv3d_tma(const float* in, const float* weight, const float* bias, f
   if ((long long)Cin * D * H * W * 4 >= (1LL << 40)) return SMILE_OK;
   {
     bool flat = false;
-    static const bool no_flat = getenv("SMILE_CONV_NO_FLAT") != nullptr;  // profiling knob
+    const bool no_flat = getenv("SMILE_CONV_NO_FLAT") != nullptr;  // tuning knob (tools/tune_conv.py), read per call
     if (!no_flat) {
       int rc = launch_conv3d_tma_flat(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st,
                                       &flat);
@@ -56,6 +57,13 @@ int launch_conv3d_tma(const float* in, const float* weight, const float* bias, f
     if (!found) {  // nothing reaches two waves: maximise the CTA count
       V = 2;
       CO = (co_cap >= 8 && ctas(2, 4) <= ctas(2, 8)) ? 8 : 4;
+    }
+  }
+  if (const char* f = getenv("SMILE_CONV_FORCE")) {  // tuning knob: "CO:V" of the register tile
+    int fco = 0, fv = 0;
+    if (sscanf(f, "%d:%d", &fco, &fv) == 2 && fco <= co_cap * 2) {
+      CO = fco;
+      V = fv;
     }
   }
   if (TWL == 32) {

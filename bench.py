@@ -92,7 +92,8 @@ class ClockSampler:
             self._thread.join()
 
     def summary(self):
-        return {"sm_mhz": (statistics.median(self.samples) if self.samples else None), "sm_max_mhz": self.max_mhz,
+        return {"sm_mhz": (statistics.median(self.samples) if self.samples else None),
+                "sm_mhz_min": (min(self.samples) if self.samples else None), "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons)}
 
 
@@ -206,6 +207,15 @@ def main():
     clk = ClockSampler(physical_device_index(local))
     clk.__enter__()                      # sampling starts with the warm-up, its samples are dropped below
     with torch.no_grad():
+        # bring the GPU out of its idle power state before the W warm-up steps (not a step of the workload: a plain
+        # matmul loop for ~0.25 s; a cold B200 otherwise spends the first timed steps ramping up)
+        pre = torch.randn(4096, 4096, device=dev)
+        t_pre = time.perf_counter()
+        while time.perf_counter() - t_pre < 0.25:
+            for _ in range(10):
+                pre = torch.tanh(pre @ pre) * 0.01
+            torch.cuda.synchronize()
+        del pre
         for _ in range(W):
             y, flow = model(moving, fixed)
         torch.cuda.synchronize()
@@ -223,7 +233,10 @@ def main():
         barrier()
         clk.__exit__()
         launches = _lib.LAUNCHES - l0
-        total_ms = reduce_max(sum(a.elapsed_time(b) for a, b in evs))
+        step_ms = [a.elapsed_time(b) for a, b in evs]
+        if os.environ.get("SMILE_BENCH_DEBUG"):
+            print("step ms:", " ".join(f"{t:.2f}" for t in step_ms), file=sys.stderr)
+        total_ms = reduce_max(sum(step_ms))
         value = world * K / (total_ms * 1e-3)
 
         # ---------------- e2e: host buffers in, host buffers out, copies inside the timed region.
@@ -365,7 +378,7 @@ def main():
                 "dtype": "f32", "data": "synthetic", "config": workload_config(1, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / K},
-                "gpu_launches": launches, "gpu_launches_per_step": launches // K, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "train": train, "batched": batched}
+                "step_ms_min_max": [min(step_ms), max(step_ms)], "gpu_launches": launches, "gpu_launches_per_step": launches // K, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "train": train, "batched": batched}
         if breakdown:
             line["kernel_ms"] = {name: round(ms, 4) for ms, _, name in breakdown[:12]}
         print(json.dumps(line))

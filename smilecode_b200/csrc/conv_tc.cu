@@ -87,7 +87,7 @@ __global__ void conv3d_tc_prep_kernel(const float* __restrict__ w, float* __rest
 
 constexpr int THREADS = 256;  // 8 warps: warps w and w + 4 share TMEM lane quadrant w and split the NT columns
 
-template <int NT, bool NORM>
+template <int NT, bool NORM, int SU>
 __global__ void __launch_bounds__(THREADS)
 conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, const float* __restrict__ bias,
                  float* __restrict__ out, const double* __restrict__ in_stats, double* __restrict__ out_stats, int Cin,
@@ -164,12 +164,13 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
     }
     // ---- stage the activations: global NCDHW -> (normalise) -> hi/lo -> position-major float4
     const int ci0 = stage * KC;
-    for (int i0 = tid; i0 < items; i0 += THREADS * 4) {
-      float v[4][4];
-      bool ok[4];
-      int cbs[4];
+    // SU items per thread in flight (template: 4 or 6, whichever covers the 6 * SEG items of a stage in one round)
+    for (int i0 = tid; i0 < items; i0 += THREADS * SU) {
+      float v[SU][4];
+      bool ok[SU];
+      int cbs[SU];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < SU; ++u) {
         const int i = i0 + u * THREADS;
         const int s = i % SEG;
         const int t = i / SEG;
@@ -187,7 +188,7 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
         for (int j = 0; j < 4; ++j) v[u][j] = (ok[u] && ci0 + cb * 4 + j < Cin) ? __ldg(p + (long long)j * N) : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < SU; ++u) {
         const int i = i0 + u * THREADS;
         if (i < items) {
           float hi[4], lo[4];
@@ -367,7 +368,9 @@ int launch_nt(const float* in, const float* weight, const float* wprep_in, const
                                   act_out, eps);
     return check_launch("conv3d(tcgen05)");
   };
-  const int rc = (in_stats != nullptr) ? run(conv3d_tc_kernel<NT, true>) : run(conv3d_tc_kernel<NT, false>);
+  const bool su6 = 3 * 2 * SEG > 4 * THREADS;  // more than four items per thread: keep six in flight (measured)
+  const int rc = (in_stats != nullptr) ? (su6 ? run(conv3d_tc_kernel<NT, true, 6>) : run(conv3d_tc_kernel<NT, true, 4>))
+                                       : (su6 ? run(conv3d_tc_kernel<NT, false, 6>) : run(conv3d_tc_kernel<NT, false, 4>));
   if (scratch != nullptr) cudaFreeAsync(scratch, st);
   return rc;
 }

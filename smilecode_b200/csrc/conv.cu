@@ -11,6 +11,7 @@
 //     ("normalise on load"), and this layer's per-(b,c) sum / sum-of-squares are reduced
 //     warp -> CTA -> one fp64 atomicAdd per channel, so a ConvInsBlock costs one read of its
 //     input and one write of its raw output.
+#include <cstdint>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -256,6 +257,7 @@ int launch_conv3d(const float* in, const float* weight, const float* bias, float
 // (optionally) AvgPool3d(2) of the result for the next pyramid level in the same pass
 // (models.py:144-150 and 198, 204, 210, 216).  One thread per 2x2x2 cell.
 // ---------------------------------------------------------------------------------------------
+template <bool EVEN>
 __global__ void __launch_bounds__(256) in_finalize_kernel(const float* __restrict__ raw, const double* __restrict__ stats,
                                                           float* __restrict__ out, float* __restrict__ pooled, int D, int H,
                                                           int W, float eps) {
@@ -276,6 +278,23 @@ __global__ void __launch_bounds__(256) in_finalize_kernel(const float* __restric
     const int ch = (int)(r % CH);
     const int cd = (int)(r / CH);
     float sum = 0.f;
+    if (EVEN) {  // all extents even: the cell is four aligned float2 rows -> coalesced 8-byte loads and stores
+      const long long o00 = ((long long)(2 * cd) * H + 2 * ch) * W + 2 * cw;
+      const long long offs[4] = {o00, o00 + W, o00 + (long long)H * W, o00 + (long long)H * W + W};
+      float2 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float2*>(rb + offs[k]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[k].x = lrelu01((v[k].x - mean) * rstd);
+        v[k].y = lrelu01((v[k].y - mean) * rstd);
+        *reinterpret_cast<float2*>(ob + offs[k]) = v[k];
+      }
+      // same summation order as the scalar path: (dz, dy, dx) lexicographic
+      sum = ((((((v[0].x + v[0].y) + v[1].x) + v[1].y) + v[2].x) + v[2].y) + v[3].x) + v[3].y;
+      if (pooled != nullptr) pooled[(long long)bc * PD * PH * PW + ((long long)cd * PH + ch) * PW + cw] = sum * 0.125f;
+      continue;
+    }
 #pragma unroll
     for (int dz = 0; dz < 2; ++dz)
 #pragma unroll
@@ -301,7 +320,12 @@ int launch_in_finalize(const float* raw, const double* stats, float* out, float*
   long long g = ceil_div_ll(cells, 256);
   const long long cap = 4096;
   dim3 grid((unsigned)(g < cap ? g : cap), B * C);
-  in_finalize_kernel<<<grid, 256, 0, st>>>(raw, stats, out, pooled, D, H, W, eps);
+  const bool even = D % 2 == 0 && H % 2 == 0 && W % 2 == 0 && (reinterpret_cast<uintptr_t>(raw) & 7u) == 0 &&
+                    (reinterpret_cast<uintptr_t>(out) & 7u) == 0;
+  if (even)
+    in_finalize_kernel<true><<<grid, 256, 0, st>>>(raw, stats, out, pooled, D, H, W, eps);
+  else
+    in_finalize_kernel<false><<<grid, 256, 0, st>>>(raw, stats, out, pooled, D, H, W, eps);
   return check_launch("in_finalize");
 }
 

@@ -88,7 +88,7 @@ struct TCfg {
 };
 
 template <int CO, int V, int TWL, int NW, int CIC, bool NORM, int FW = 0>
-__global__ void __launch_bounds__(NW * 32, (NW * 32 <= 128) ? 4 : 2)
+__global__ void __launch_bounds__(NW * 32, (NW * 32 <= 128) ? 4 : ((CO == 4 && CIC == 1) ? 3 : 2))
 conv3d_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ weight,
                   const float* __restrict__ bias, float* __restrict__ out, const double* __restrict__ in_stats,
                   double* __restrict__ out_stats, int Cin, int Cout, int D, int H, int W, int tiles_h, int tiles_w,

@@ -173,6 +173,46 @@ def test_conv_flat_tiles_norm_on_load(ops, cin, cout, shape):
     assert torch.allclose(st2[..., 1], (ref.double() ** 2).sum(dim=(2, 3, 4)), rtol=1e-4, atol=1e-2)
 
 
+def test_conv_tensor_core_path_forced_on_all_shapes():
+    """SMILE_CONV_TC=2 sends every layer with >= 12 output channels through the tcgen05 kernel (by default only the
+    coarse levels use it): wide rows, few input channels, partial tiles, batch 2, normalise-on-load, LeakyReLU output.
+    The switch is read once per process, so the check runs in a child process."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, torch
+sys.path.insert(0, '.')
+from oracle import modet_oracle as orc
+from smilecode_b200 import ops
+g = torch.Generator().manual_seed(21)
+worst = 0.0
+for cin, cout, shape in [(8, 16, (5, 7, 80)), (6, 12, (4, 9, 33)), (16, 16, (3, 12, 64)), (3, 20, (6, 5, 26)),
+                         (24, 48, (4, 6, 20)), (40, 36, (3, 4, 10))]:
+    x = torch.randn(2, cin, *shape, generator=g)
+    w1 = torch.randn(cin, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5
+    w2 = torch.randn(cout, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5
+    b1, b2 = torch.randn(cin, generator=g) * 0.1, torch.randn(cout, generator=g) * 0.1
+    r1 = orc.conv3(x, w1, b1)
+    ref = orc.conv3(orc.lrelu(orc.instance_norm(r1)), w2, b2)
+    raw, st = ops.conv3d(x.cuda(), w1.cuda(), b1.cuda(), want_stats=True)
+    out, st2 = ops.conv3d(raw, w2.cuda(), b2.cuda(), in_stats=st, want_stats=True)
+    act, _ = ops.conv3d(raw, w2.cuda(), b2.cuda(), in_stats=st, act_out=True)
+    e = float((out.cpu() - ref).abs().max() / ref.abs().max())
+    e = max(e, float((act.cpu() - orc.lrelu(ref)).abs().max() / ref.abs().max()))
+    s = st2.cpu().reshape(2, cout, 2)
+    assert torch.allclose(s[..., 0], ref.double().sum(dim=(2, 3, 4)), rtol=1e-4, atol=1e-2), (cin, cout, shape)
+    assert torch.allclose(s[..., 1], (ref.double() ** 2).sum(dim=(2, 3, 4)), rtol=1e-4, atol=1e-2), (cin, cout, shape)
+    worst = max(worst, e)
+print('worst relative error', worst)
+assert worst <= 1e-5, worst
+"""
+    env = dict(os.environ, SMILE_CONV_TC="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 def test_conv_prepared_weight_cache(ops):
     """Tensor-core conv with weights prepared once per nn.Parameter (inference): same result as the per-call path,
     and the cache follows in-place updates of the parameter."""

@@ -4,14 +4,15 @@
 //   flow_out = post * (SpatialTransformer(flow_in, w) + w)  models.py:403 / 408 (49-67)
 //   moved    = SpatialTransformer(moving, flow_out)         models.py:410
 //
-// A CTA marches a column of TH rows x 32 voxels along D.  One producer warp streams, per plane,
-// three TMA boxes into an mbarrier ring: the key plane with its 1-voxel halo (out-of-volume
-// elements are zero-filled by TMA == the zero padding of models.py:319), the query plane and the
-// three flow_in planes with halo.  TH consumer warps (lanes along W) keep the partial logits of
-// the three voxels a key plane contributes to in registers, so each 24-byte key row is read
-// from shared memory once (9 rows per output voxel instead of 27); dot products are packed
-// fma.rn.f32x2.  |w| <= 1, so the compose sample lives in the same 3x3x3 window and is gathered
-// from the flow ring (global-memory path when a corner leaves the window, i.e. |w| == 1).
+// A CTA of TH warps marches a column of TH rows x 32 voxels along D.  Per plane three TMA boxes land in an mbarrier
+// ring: the key plane with its 1-voxel halo (out-of-volume elements are zero-filled by TMA == the zero padding of
+// models.py:319), the query plane and the three flow_in planes with halo.  There is no producer warp: every warp
+// releases a ring slot with an mbarrier arrive, and whichever warp first sees a slot released by all claims the next
+// stage (CAS) and issues its TMA loads.  Lanes run along W.  A key plane holds tap plane 2 of the oldest in-flight
+// voxel, 1 of the middle one and 0 of the newest: every 24-byte key row is read from shared memory once and its nine
+// logits per voxel are folded into a running (online) softmax state, so no logits are kept across planes.  Dot
+// products and lerps are packed fma.rn.f32x2.  |w| <= 1, so the compose sample lives in the same 3x3x3 window and is
+// gathered from the flow ring (global-memory path when a corner leaves the window, i.e. |w| == 1).
 #include <cuda.h>
 #include <cudaTypedefs.h>
 

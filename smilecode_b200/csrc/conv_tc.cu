@@ -212,7 +212,7 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
     __syncthreads();
 
-    // ---- one thread issues the 81 MMAs of the stage
+    // ---- one thread issues the 54 MMAs of the stage (two per tap)
     if (tid == 0) {
       mbar_wait(smem_u32(bars), ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -240,7 +240,7 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bars + 1))
                    : "memory");
     }
-    // ---- drain the eight accumulators into registers (round-to-nearest adds)
+    // ---- drain the accumulator groups into registers (round-to-nearest adds)
     mbar_wait(smem_u32(bars + 1), ph);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll

@@ -6,6 +6,8 @@
 // tap is a fully used contiguous segment), the 27 logits + softmax + the three signed sums of
 // "attn @ V" never leave the register file.  Zero-padded taps keep logit = rpb (models.py:319).
 // The TMA-tiled fast path for the large heads==1 levels lives in attn_tma.cu.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -20,6 +22,8 @@ __device__ __forceinline__ float fast_exp2(float x) {
 constexpr float kLog2e = 1.4426950408889634f;
 
 // Softmax over the 27 logits (already scaled by log2 e) and expectation of the tap offsets.
+// EXACT: exp2f() (full-accuracy) instead of ex2.approx -- the bisect knob SMILE_ATTN_EXACT=1 (tools/parity_bisect.py).
+template <bool EXACT = false>
 __device__ __forceinline__ void softmax_expect(const float (&lg)[27], float& od, float& oh, float& ow) {
   float m = lg[0];
 #pragma unroll
@@ -27,7 +31,7 @@ __device__ __forceinline__ void softmax_expect(const float (&lg)[27], float& od,
   float sum = 0.f, sd = 0.f, sh = 0.f, sw = 0.f;
 #pragma unroll
   for (int t = 0; t < 27; ++t) {
-    float p = fast_exp2(lg[t] - m);
+    float p = EXACT ? exp2f(lg[t] - m) : fast_exp2(lg[t] - m);
     sum += p;
     const int ti = t / 9 - 1, tj = (t / 3) % 3 - 1, tk = t % 3 - 1;
     if (ti != 0) sd += (ti > 0 ? p : -p);
@@ -84,7 +88,7 @@ __device__ __forceinline__ void logits_from_global(const float* __restrict__ q, 
 }
 
 // q,k [B,D,H,W,heads*hd] channels-last -> out [B,3*heads,D,H,W]
-template <int HD>
+template <int HD, bool EXACT = false>
 __global__ void __launch_bounds__(128) attn_generic_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                            const float* __restrict__ rpb, float* __restrict__ out, int D,
                                                            int H, int W, int heads, int hd, float qscale) {
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(128) attn_generic_kernel(const float* __restri
     logits_from_global<HD>(qb + p * C + head * hd, kb + p * C + head * hd, s_rpb + head * 27, hd, C, d, h, w, D, H, W,
                            qscale, lg);
     float od, oh, ow;
-    softmax_expect(lg, od, oh, ow);
+    softmax_expect<EXACT>(lg, od, oh, ow);
     float* o = ob + (long long)head * 3 * N + p;
     o[0] = od;
     o[N] = oh;
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(128) attn_generic_kernel(const float* __restri
 
 // Generic (no TMA) fused heads==1 level: attention -> flow compose -> optional warp of `moving`.
 //   w = attn(q,k);  f' = post * (T(flow_in, w) + w);  moved[c] = T(moving[c], f')
-template <int HD>
+template <int HD, bool EXACT = false>
 __global__ void __launch_bounds__(128) fused_generic_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                             const float* __restrict__ rpb, const float* __restrict__ flow_in,
                                                             const float* __restrict__ moving, float* __restrict__ flow_out,
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(128) fused_generic_kernel(const float* __restr
     float lg[27];
     logits_from_global<HD>(qb + p * hd, kb + p * hd, s_rpb, hd, hd, d, h, w, D, H, W, qscale, lg);
     float w0, w1, w2;
-    softmax_expect(lg, w0, w1, w2);
+    softmax_expect<EXACT>(lg, w0, w1, w2);
     TriSample s;
     tri_setup(s, st_coord(d, w0, dm1), st_coord(h, w1, hm1), st_coord(w, w2, wm1), D, H, W);
     const float f0 = __fmul_rn(post, __fadd_rn(tri_gather(s, fb), w0));
@@ -169,9 +173,16 @@ static inline int grid1d(long long n, int block) {
   return (int)(g < cap ? g : cap);
 }
 
+// bisect knob, read per call: 1 = generic kernels with full-accuracy exp2f (no TMA path, no ex2.approx)
+static inline bool attn_exact() {
+  const char* e = getenv("SMILE_ATTN_EXACT");
+  return e != nullptr && e[0] == '1';
+}
+
 int launch_modet_attn(const float* q, const float* k, const float* rpb, float* out, int B, int D, int H, int W, int heads,
                       int hd, float scale, cudaStream_t st) {
-  if (heads == 1 && hd == 6) {
+  const bool exact = attn_exact();
+  if (heads == 1 && hd == 6 && !exact) {
     bool handled = false;
     int rc = launch_modet_attn_tma(q, k, rpb, nullptr, nullptr, out, nullptr, nullptr, B, D, H, W, scale, 1.0f, 0, st, &handled);
     if (handled) return rc;
@@ -179,7 +190,11 @@ int launch_modet_attn(const float* q, const float* k, const float* rpb, float* o
   const long long total = (long long)D * H * W * heads;
   dim3 grid(grid1d(total, 128), B);
   size_t smem = (size_t)heads * 27 * sizeof(float);
-  if (hd == 6)
+  if (exact && hd == 6)
+    attn_generic_kernel<6, true><<<grid, 128, smem, st>>>(q, k, rpb, out, D, H, W, heads, hd, scale * kLog2e);
+  else if (exact)
+    attn_generic_kernel<0, true><<<grid, 128, smem, st>>>(q, k, rpb, out, D, H, W, heads, hd, scale * kLog2e);
+  else if (hd == 6)
     attn_generic_kernel<6><<<grid, 128, smem, st>>>(q, k, rpb, out, D, H, W, heads, hd, scale * kLog2e);
   else if (hd == 4)
     attn_generic_kernel<4><<<grid, 128, smem, st>>>(q, k, rpb, out, D, H, W, heads, hd, scale * kLog2e);
@@ -193,7 +208,7 @@ int launch_modet_attn(const float* q, const float* k, const float* rpb, float* o
 int launch_modet_fused(const float* q, const float* k, const float* rpb, const float* flow_in, const float* moving,
                        float* flow_out, float* moved, int B, int D, int H, int W, int hd, float scale, float post,
                        int Cmov, cudaStream_t st) {
-  if (hd == 6) {
+  if (hd == 6 && !attn_exact()) {
     bool handled = false;
     int rc = launch_modet_attn_tma(q, k, rpb, flow_in, moving, nullptr, flow_out, moved, B, D, H, W, scale, post, Cmov, st,
                                    &handled);
@@ -201,7 +216,10 @@ int launch_modet_fused(const float* q, const float* k, const float* rpb, const f
   }
   const long long N = (long long)D * H * W;
   dim3 grid(grid1d(N, 128), B);
-  if (hd == 6)
+  if (attn_exact())
+    fused_generic_kernel<0, true><<<grid, 128, 0, st>>>(q, k, rpb, flow_in, moving, flow_out, moved, D, H, W, hd,
+                                                        scale * kLog2e, post, Cmov);
+  else if (hd == 6)
     fused_generic_kernel<6><<<grid, 128, 0, st>>>(q, k, rpb, flow_in, moving, flow_out, moved, D, H, W, hd, scale * kLog2e,
                                                   post, Cmov);
   else

@@ -18,6 +18,11 @@ from torch.distributions.normal import Normal
 
 from . import ops
 
+# Debug / bisect switch (tools/parity_bisect.py): False runs levels 2 and 1 as the reference spells them
+# (attention -> SpatialTransformer(flow, w) + w -> upsample / final warp: the stand-alone bit-exact kernels)
+# instead of the fused single-head kernel.
+FUSE_LEVELS = True
+
 __all__ = ["SpatialTransformer", "VecInt", "ResizeTransform", "ConvBlock", "ConvInsBlock", "UpConvBlock",
            "DeconvBlock", "Encoder", "ProjectionLayer", "CWM", "ModeTransformer", "ModeT", "ModeT_cu"]
 
@@ -37,10 +42,16 @@ class SpatialTransformer(nn.Module):
         self.register_buffer("grid", _voxel_grid(size))
 
     def forward(self, src, flow):
-        if self.mode != "bilinear":
-            raise NotImplementedError("SpatialTransformer: only mode='bilinear' is on the ModeT hot path")
         if flow.dim() != 5:
             raise NotImplementedError("SpatialTransformer: only 3-D volumes are supported")
+        if self.mode == "nearest":        # utils.register_model(img_size, 'nearest') (ModeT/utils.py:74-83, infer.py:66)
+            from .metrics import warp3d_nearest
+            return warp3d_nearest(src, flow)
+        if self.mode != "bilinear":
+            raise NotImplementedError(f"SpatialTransformer: mode {self.mode!r} is not on the ModeT path")
+        if torch.is_grad_enabled() and (src.requires_grad or flow.requires_grad):
+            from . import autograd as ag
+            return ag.Warp.apply(src, flow)
         return ops.warp3d(src, flow)
 
 
@@ -272,6 +283,12 @@ class ModeT(nn.Module):
         w = self.cwm3(self._attend(3, Fx[2], M[2], flow))
         flow = ops.flow_compose(ops.upsample2x(flow, 2.0), w)
 
+        if not FUSE_LEVELS:
+            w = self._attend(2, Fx[1], M[1], flow)
+            flow = ops.upsample2x(ops.flow_compose(flow, w), 2.0)
+            w = self._attend(1, Fx[0], M[0], flow)
+            flow = ops.flow_compose(flow, w)
+            return ops.warp3d(moving, flow), flow
         # level 2, 1: single head, attention + compose (+ final warp) fused (models.py:400-410)
         pb, mdt = self.projblock2, self.mdt2
         f2, _ = ops.modet_fused(pb(Fx[1]), pb.of_warped(M[1], flow), mdt.rpb if mdt.use_rpb else None, flow, None,

@@ -28,8 +28,9 @@ def _chk(t: Tensor, name: str, ndim: int, dtype=torch.float32) -> Tensor:
         raise SmileError(f"{name} must have {ndim} dims, got shape {tuple(t.shape)}")
     if t.requires_grad and torch.is_grad_enabled():
         raise NotImplementedError(
-            f"{name} requires grad: the backward kernels of smilecode_b200 are not built yet; "
-            "wrap the call in torch.no_grad()")
+            f"{name} requires grad: smilecode_b200.ops are the raw forward kernels; differentiable calls go through "
+            "smilecode_b200.autograd (ModeT.forward does this by itself when grad is enabled), or wrap the call in "
+            "torch.no_grad()")
     if not t.is_contiguous():
         t = t.contiguous()
     if t.data_ptr() % 16 != 0:

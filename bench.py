@@ -1,16 +1,19 @@
 #!/usr/bin/env python
 """Benchmark of the ModeT registration hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--breakdown]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config lpba|mindboggle]
+                    [--train-batch B] [--breakdown] [--comparators]
 
-One "step" = ModeT.forward on one synthetic LPBA-shape pair per GPU (160x192x160 fp32,
-BASELINE.json configs[1]).  N > 1 is launched by torchrun, one rank per GPU; pairs are independent,
-so ranks share nothing on the data path (weak scaling, no collective); the only communication is
-the max-over-ranks of the timed region.  Prints ONE JSON line on rank 0.
+One "step" = ModeT.forward on one synthetic pair per GPU: `--config lpba` (default) is BASELINE.json configs[1]
+(160x192x160 fp32, heads [8,4,2,1,1]); `--config mindboggle` is the configs[4] shape (160x192x224 fp32 with the 6-head
+level list [6,6,6,1,1]: levels 2 and 1 have no CWM in ModeT, so their head count is 1 -- SURVEY 8).  N > 1 is launched by
+torchrun, one rank per GPU; pairs are independent, so ranks share nothing on the data path (weak scaling, no collective);
+the only communication is the max-over-ranks of the timed region.  Prints ONE JSON line on rank 0.
 
-`--impl reference` times the reference's CPU implementation of the same path on the host cores.
-/root/reference does not exist on the GPU box, so that arm runs the oracle port
-(oracle/modet_oracle.py with the torch library calls the reference itself makes).
+`--impl reference` times the reference's own CPU implementation of the same path on the host cores: the UNMODIFIED
+`ModeT/models.py` from the staged reference tree (baseline/_ref, written by oracle/stage_reference.py; kind "reference")
+when it is there, otherwise the oracle port (oracle/modet_oracle.py with the torch library calls the reference itself
+makes; kind "port").
 """
 from __future__ import annotations
 
@@ -27,11 +30,27 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-SHAPE = (160, 192, 160)
-HEADS = [8, 4, 2, 1, 1]
+CONFIGS = {
+    "lpba": {"shape": (160, 192, 160), "heads": [8, 4, 2, 1, 1],
+             "workload": "LPBA-shape 160x192x160 fp32 pair, full ModeT forward (encoder + 5-level decoder), "
+                         "head_dim 6, heads [8,4,2,1,1], scale 1 (BASELINE.json configs[1])"},
+    "mindboggle": {"shape": (160, 192, 224), "heads": [6, 6, 6, 1, 1],
+                   "workload": "Mindboggle-shape 160x192x224 fp32 pair, full ModeT forward, head_dim 6, 6-head level list "
+                               "[6,6,6,1,1] (levels 2 and 1 have no CWM, so 1 head), scale 1 (BASELINE.json configs[4] shape)"},
+}
+SHAPE = CONFIGS["lpba"]["shape"]
+HEADS = CONFIGS["lpba"]["heads"]
+WORKLOAD = CONFIGS["lpba"]["workload"]
 METRIC = "volume-pairs/sec at 160x192x160 (ModeT forward, fp32)"
 UNIT = "pairs/s"
 FUSED_L1_BYTES_PER_VOXEL = 80      # q 24 + k 24 + flow 12 + moving 4 read; flow' 12 + moved 4 written
+
+
+def select_config(name: str):
+    global SHAPE, HEADS, WORKLOAD, METRIC
+    c = CONFIGS[name]
+    SHAPE, HEADS, WORKLOAD = c["shape"], c["heads"], c["workload"]
+    METRIC = f"volume-pairs/sec at {SHAPE[0]}x{SHAPE[1]}x{SHAPE[2]} (ModeT forward, fp32)"
 
 
 def measured_peaks():
@@ -107,24 +126,43 @@ def physical_device_index(local: int) -> int:
     return local
 
 
+def reference_forward_fn(sd):
+    """(callable(moving, fixed) -> (moved, flow), kind, description): the staged reference's own ModeT when available."""
+    from oracle import modet_oracle as orc
+    try:
+        from oracle import reference_loader as rl
+        ref = rl.reference_models()
+    except Exception:
+        ref = None
+    if ref is not None:
+        m = ref.ModeT(SHAPE, head_dim=6, num_heads=HEADS, scale=1)
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        assert not unexpected and all(k.endswith("grid") for k in missing), (missing, unexpected)
+        m.eval()
+        return (lambda a, b: m(a, b)), "reference", "the reference's own ModeT/models.py (unmodified, staged under baseline/_ref)"
+    fn = lambda a, b: orc.modet_forward(a, b, sd, num_heads=HEADS, scale=1.0, library_ops=True)
+    return fn, "port", "oracle port with torch library ops (reference tree not staged on this box)"
+
+
 def cpu_reference_run(steps: int, warmup: int):
-    """The reference's CPU path (oracle port, library ops) on all host cores: full pairs."""
+    """The reference's CPU path on all host cores: full pairs."""
     from oracle import modet_oracle as orc
     from smilecode_b200.synth import make_pair
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = orc.synth_state_dict(seed=1234, num_heads=HEADS)
+    fn, kind, desc = reference_forward_fn(sd)
     moving, fixed = make_pair(SHAPE, batch=1, seed=24)
     with torch.no_grad():
         small = make_pair((32, 32, 32), batch=1, seed=24)
         orc.modet_forward(*small, sd, num_heads=HEADS, scale=1.0, library_ops=True)        # thread-pool warm-up
         for _ in range(warmup):
-            orc.modet_forward(moving, fixed, sd, num_heads=HEADS, scale=1.0, library_ops=True)
+            fn(moving, fixed)
         t0 = time.perf_counter()
         for _ in range(steps):
-            orc.modet_forward(moving, fixed, sd, num_heads=HEADS, scale=1.0, library_ops=True)
+            fn(moving, fixed)
         dt = time.perf_counter() - t0
-    return steps / dt, dt / steps, cores, torch.get_num_threads()
+    return steps / dt, dt / steps, cores, torch.get_num_threads(), kind, desc
 
 
 def run_reference(args):
@@ -133,20 +171,60 @@ def run_reference(args):
         return
     steps = max(1, min(args.steps, 3))
     warm = 1 if args.warmup > 0 else 0
-    pps, spp, cores, threads = cpu_reference_run(steps, warm)
-    sample = f"{steps} full 160x192x160 pair(s) after {warm} warm-up, oracle port with torch library ops, {threads} threads"
+    pps, spp, cores, threads, kind, desc = cpu_reference_run(steps, warm)
+    sample = f"{steps} full {SHAPE[0]}x{SHAPE[1]}x{SHAPE[2]} pair(s) after {warm} warm-up, {desc}, {threads} threads"
     line = {"impl": "reference", "metric": METRIC, "value": pps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": spp * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(1, args.gpus),
-            "cpu_baseline": {"value": pps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": pps, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
+def gpu_comparators(model, moving, fixed, dev):
+    """The staged reference on this GPU, same pair and weights (informational; None entries when pieces are missing)."""
+    out = {"ref_eager_ms": None, "ref_cu_ms": None}
+    try:
+        from oracle import reference_loader as rl
+    except Exception:
+        return out
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+    def timed(m):
+        m = m.to(dev).eval()
+        with torch.no_grad():
+            for _ in range(2):
+                m(moving, fixed)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                m(moving, fixed)
+            b.record()
+            torch.cuda.synchronize()
+        return a.elapsed_time(b) / 3
+
+    for key, loader, cls in (("ref_eager_ms", rl.reference_models, "ModeT"), ("ref_cu_ms", rl.reference_models_cu, "ModeT_cu")):
+        try:
+            mod = loader()
+            if mod is None:
+                continue
+            m = getattr(mod, cls)(SHAPE, head_dim=6, num_heads=HEADS, scale=1)
+            m.load_state_dict(sd, strict=False)
+            out[key] = timed(m)
+            del m
+            torch.cuda.empty_cache()
+        except Exception as e:           # informational leg: never fail the bench
+            out[key + "_error"] = repr(e)[:200]
+    out["note"] = "reference ModeT in PyTorch eager (TF32 off) and ModeT-cu with its own modet extension (sm_100 build), ms per forward"
+    return out
+
+
 def workload_config(batch_per_gpu: int, n_gpus: int):
-    return {"workload": "LPBA-shape 160x192x160 fp32 pair, full ModeT forward (encoder + 5-level decoder), "
-                        "head_dim 6, heads [8,4,2,1,1], scale 1 (BASELINE.json configs[1])",
+    return {"workload": WORKLOAD,
             "pairs_per_gpu_per_step": batch_per_gpu, "global_pairs_per_step": batch_per_gpu * n_gpus,
             "parallelism": f"replicas x{n_gpus} (pairs sharded by batch, no data-path collective)",
             "l2": "flushed between timed steps (256 MiB memset outside the timed events); per-step working set >> 126 MB L2"}
@@ -161,7 +239,12 @@ def main():
     ap.add_argument("--breakdown", action="store_true", help="print a per-kernel CUDA-event breakdown to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
+    ap.add_argument("--config", default="lpba", choices=sorted(CONFIGS))
+    ap.add_argument("--train-batch", type=int, default=1, help="pairs per GPU in the training-step leg")
+    ap.add_argument("--comparators", action="store_true",
+                    help="also time the staged reference on this GPU (PyTorch eager, and ModeT-cu with its own extension)")
     args = ap.parse_args()
+    select_config(args.config)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -243,39 +326,63 @@ def main():
 
         # ---------------- e2e: host buffers in, host buffers out, copies inside the timed region.
         # The public host-to-host API is smilecode_b200.pipeline.RegistrationPipeline (upload / compute / download
-        # streams, 2 slots): every step uploads the pair from pinned host memory and downloads moved + flow.
+        # streams, 3 slots).  Headline mode = what the reference's loop moves per pair (infer.py:79-89): the pair goes up from
+        # pinned host memory, the deformation field comes back into pinned host memory.  Two more modes are reported next
+        # to it: both outputs of ModeT.forward down (round-1 behaviour), and metrics-only (the Jacobian fold count of
+        # infer.py:89-90 evaluated on the device by smilecode_b200.metrics: 8 bytes down).
+        from smilecode_b200 import metrics as smetrics
         from smilecode_b200.pipeline import RegistrationPipeline
-        pipe = RegistrationPipeline(model, SHAPE, depth=2, device=dev)
+
+        def time_pipeline(pipe):
+            for _ in pipe.run([(moving_h, fixed_h)] * 3):
+                pass
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            n_out, last = 0, None
+            for last in pipe.run([(moving_h, fixed_h)] * K):
+                n_out += 1
+            pipe.s_out.synchronize()
+            e1.record(stream)
+            barrier()
+            assert n_out == K
+            ms = reduce_max(e0.elapsed_time(e1))
+            return world * K / (ms * 1e-3), ms / K, last
+
+        pipe = RegistrationPipeline(model, SHAPE, depth=3, device=dev, outputs=("flow",))
         h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
-        for _ in pipe.run([(moving_h, fixed_h)] * 3):
-            pass
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        n_out = 0
-        for y_h, flow_h in pipe.run([(moving_h, fixed_h)] * K):
-            n_out += 1
-        pipe.s_out.synchronize()
-        e1.record(stream)
-        barrier()
-        assert n_out == K
-        e2e_ms = reduce_max(e0.elapsed_time(e1))
-        e2e_value = world * K / (e2e_ms * 1e-3)
+        e2e_value, e2e_ms_step, flow_h = time_pipeline(pipe)
         flow_h = flow_h.clone()
+        del pipe
+        e2e_modes = {}
+        pipe = RegistrationPipeline(model, SHAPE, depth=3, device=dev, outputs=("moved", "flow"))
+        v, ms, _ = time_pipeline(pipe)
+        e2e_modes["moved+flow"] = {"value": v, "ms_per_step": ms, "d2h_bytes_per_step": pipe.d2h_bytes}
+        del pipe
+        pipe = RegistrationPipeline(model, SHAPE, depth=3, device=dev, outputs=(),
+                                    reduce=lambda moved, flow, extra: smetrics.jacobian_determinant_vxm(flow, want_det=False)[1])
+        v, ms, _ = time_pipeline(pipe)
+        e2e_modes["metrics_only"] = {"value": v, "ms_per_step": ms, "d2h_bytes_per_step": 8,
+                                     "what": "non-positive Jacobian count of infer.py:89-90 computed on the device"}
+        del pipe
+        torch.cuda.empty_cache()
 
         # ---------------- roofline of the headline kernel: fused L1 attention + compose + warp
         N1 = SHAPE[0] * SHAPE[1] * SHAPE[2]
         g = torch.Generator(device=dev).manual_seed(7)
-        q1 = torch.randn(1, *SHAPE, 6, device=dev, generator=g)
-        k1 = torch.randn(1, *SHAPE, 6, device=dev, generator=g)
+        pb1 = model.projblock1
+        lnp = {"ln_gamma": pb1.norm.weight.detach(), "ln_beta": pb1.norm.bias.detach()}   # as ModeT.forward calls it
+        lnf = lambda t: torch.nn.functional.layer_norm(t, (6,), lnp["ln_gamma"], lnp["ln_beta"])
+        q1 = lnf(torch.randn(1, *SHAPE, 6, device=dev, generator=g))
+        k1 = lnf(torch.randn(1, *SHAPE, 6, device=dev, generator=g))
         rpb1 = model.mdt1.rpb.detach()
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
         for _ in range(3):
-            ops.modet_fused(q1, k1, rpb1, flow, moving, 1.0, 1.0)
+            ops.modet_fused(q1, k1, rpb1, flow, moving, 1.0, 1.0, **lnp)
         for a, b in kev:
             flush.zero_()
             a.record(stream)
-            ops.modet_fused(q1, k1, rpb1, flow, moving, 1.0, 1.0)
+            ops.modet_fused(q1, k1, rpb1, flow, moving, 1.0, 1.0, **lnp)
             b.record(stream)
         torch.cuda.synchronize()
         k_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
@@ -286,6 +393,8 @@ def main():
             with open(os.path.join(ROOT, "profiles", "fused_l1_traffic.json")) as f:
                 tj = json.load(f)
             traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj["source"]
+            if tuple(tj.get("shape", CONFIGS["lpba"]["shape"])) != tuple(SHAPE):
+                traffic, traffic_src = None, None          # the capture is of the LPBA shape
         except Exception:
             pass
         roofline = {"kernel": "modet_fused_fwd (L1: attention heads=1 + flow compose + warp moving)", "bound": "hbm",
@@ -332,6 +441,10 @@ def main():
         randomize_weights(tmodel, seed=1234)
         tmodel = tmodel.to(dev)
         trainer = Trainer(tmodel, lr=1e-4, distributed=world > 1)
+        TB = max(1, args.train_batch)
+        if TB > 1:
+            mvs, fxs = zip(*[make_pair(SHAPE, batch=1, seed=24 + rank + 100 * i) for i in range(TB)])
+            moving, fixed = torch.cat(mvs).to(dev), torch.cat(fxs).to(dev)
         for _ in range(2):
             trainer.step(moving, fixed)
         barrier()
@@ -344,9 +457,10 @@ def main():
         t1.record(stream)
         barrier()
         tms = reduce_max(t0.elapsed_time(t1)) / TK
-        train = {"value": world * 1e3 / tms, "unit": "pairs/s", "ms_per_step": tms, "steps": TK,
+        train = {"value": world * TB * 1e3 / tms, "unit": "pairs/s", "ms_per_step": tms, "steps": TK,
+                 "pairs_per_gpu_per_step": TB, "global_pairs_per_step": TB * world, "dtype": "f32",
                  "gpu_launches_per_step": (_lib.LAUNCHES - l0) // TK, "loss": float(tloss),
-                 "config": "fp32 training step, 1 pair per GPU, NCC_vxm(9) + Grad3d(l2), Adam(amsgrad); "
+                 "config": f"fp32 training step, {TB} pair(s) per GPU, NCC_vxm(9) + Grad3d(l2), Adam(amsgrad); "
                            + ("flat-bucket NCCL gradient all-reduce" if world > 1 else "single GPU, no collective")}
         del trainer, tmodel
         torch.cuda.empty_cache()
@@ -357,30 +471,39 @@ def main():
         from oracle import modet_oracle as orc     # checker / CPU baseline leg only
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
+        ref_fn, kind, desc = reference_forward_fn(sd)
         with torch.no_grad():
             small = make_pair((32, 32, 32), batch=1, seed=24)
             orc.modet_forward(*small, sd, num_heads=HEADS, scale=1.0, library_ops=True)
             t0 = time.perf_counter()
-            y_ref, flow_ref = orc.modet_forward(moving_h, fixed_h, sd, num_heads=HEADS, scale=1.0, library_ops=True)
+            y_ref, flow_ref = ref_fn(moving_h, fixed_h)
             dt = time.perf_counter() - t0
             # same pair in fp64 (not timed): the exact answer both fp32 paths are measured against
             sd64 = {k: v.double() for k, v in sd.items()}
             _, flow_ref64 = orc.modet_forward(moving_h.double(), fixed_h.double(), sd64, num_heads=HEADS, scale=1.0,
                                               library_ops=True)
         err = float((flow_h - flow_ref).abs().max())
-        cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"1 full 160x192x160 pair ({dt:.1f} s), oracle port with torch library ops",
-               "max_abs_flow_diff_vs_gpu": err,
+        cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+               "sample": f"1 full {SHAPE[0]}x{SHAPE[1]}x{SHAPE[2]} pair ({dt:.1f} s), {desc}",
+               "max_abs_flow_diff_vs_gpu": err, "rel_flow_diff_vs_gpu": err / float(flow_ref64.abs().max()),
                "max_abs_flow_err_vs_fp64": {"gpu": float((flow_h.double() - flow_ref64).abs().max()),
                                             "cpu_fp32": float((flow_ref.double() - flow_ref64).abs().max())}}
+
+    # ---------------- informational GPU comparators: the staged reference on this GPU
+    comparators = None
+    if args.comparators and rank == 0 and world == 1:
+        comparators = gpu_comparators(model, moving, fixed, dev)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(1, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms / K},
-                "step_ms_min_max": [min(step_ms), max(step_ms)], "gpu_launches": launches, "gpu_launches_per_step": launches // K, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "train": train, "batched": batched}
+                        "ms_per_step": e2e_ms_step,
+                        "what": "RegistrationPipeline(outputs=('flow',)): pair up from pinned host memory, flow down into "
+                                "pinned host memory (what infer.py:79-89 moves per pair)", "other_modes": e2e_modes},
+                "step_ms_min_max": [min(step_ms), max(step_ms)], "gpu_launches": launches, "gpu_launches_per_step": launches // K, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "train": train, "batched": batched,
+                "comparators": comparators}
         if breakdown:
             line["kernel_ms"] = {name: round(ms, 4) for ms, _, name in breakdown[:12]}
         print(json.dumps(line))

@@ -65,12 +65,17 @@ int smile_flow_compose_fwd(const float* flow, const float* w, float* out, int B,
  *   flow_out = postmul * (SpatialTransformer(flow_in, w) + w)
  *   moved    = SpatialTransformer(moving, flow_out)       (skipped when moved == NULL)
  * q, k: channels-last [B,D,H,W,head_dim]; flow_in/flow_out: [B,3,D,H,W]; moving/moved: [B,Cmov,D,H,W].
- * Numerics: the softmax uses ex2.approx and is accumulated tap plane by tap plane (online softmax), the two trilinear
- * samples are separable lerps -- equal to the three separate calls within ~1e-5 absolute (tolerance-checked, 1e-4), not
- * bit for bit; smile_warp3d_fwd and smile_flow_compose_fwd are the bit-exact forms. */
-int smile_modet_fused_fwd(const float* q, const float* k, const float* rpb, const float* flow_in, const float* moving,
-                          float* flow_out, float* moved, int B, int D, int H, int W, int head_dim, float scale,
-                          float postmul, int Cmov, smile_stream_t stream);
+ * ln_gamma, ln_beta: optional (both or neither) device pointers to the head_dim LayerNorm affine parameters of the
+ * ProjectionLayer that produced BOTH q and k (models.py:233, 240).  They are a promise about the inputs, not an operand:
+ * |LayerNorm(x)|_2 <= sqrt(head_dim), so |logit| <= |scale| * (max|gamma| * sqrt(head_dim) + |beta|_2)^2 + max|rpb|; the
+ * kernel evaluates that bound and, when it is far inside the fp32 exponent range, sums the exponentials without a running
+ * maximum.  NULL (or a large bound, or non-finite parameters) selects the online-maximum softmax, valid for any q, k.
+ * Numerics: ex2.approx exponentials accumulated tap plane by tap plane, the two trilinear samples are separable lerps --
+ * equal to the three separate calls within ~1e-5 absolute (tolerance-checked, 1e-4), not bit for bit; smile_warp3d_fwd
+ * and smile_flow_compose_fwd are the bit-exact forms. */
+int smile_modet_fused_fwd(const float* q, const float* k, const float* rpb, const float* ln_gamma, const float* ln_beta,
+                          const float* flow_in, const float* moving, float* flow_out, float* moved, int B, int D, int H,
+                          int W, int head_dim, float scale, float postmul, int Cmov, smile_stream_t stream);
 
 /* a7  ProjectionLayer.forward (ModeT/models.py:238-241): channels-first feat [B,Cin,N] ->
  * LayerNorm(Linear(feat)) channels-last [B,N,C].  weight: [C,Cin]; bias, gamma, beta: [C]. */

@@ -18,7 +18,7 @@ SIGNATURES = {
     "smile_warp3d_fwd": [P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     "smile_upsample2x_fwd": [P, P, c_int, c_int, c_int, c_int, c_int, c_float, P],
     "smile_flow_compose_fwd": [P, P, P, c_int, c_int, c_int, c_int, c_float, P],
-    "smile_modet_fused_fwd": [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, P],
+    "smile_modet_fused_fwd": [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, P],
     "smile_proj_ln_fwd": [P, P, P, P, P, P, c_int, c_int, c_int, c_longlong, c_float, P],
     "smile_warp_proj_ln_fwd": [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P],
     "smile_conv3d_fwd": [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P],

@@ -166,6 +166,15 @@ __global__ void __launch_bounds__(128) fused_generic_kernel(const float* __restr
 int launch_modet_attn_tma(const float* q, const float* k, const float* rpb, const float* flow_in, const float* moving,
                           float* w_out, float* flow_out, float* moved, int B, int D, int H, int W, float scale, float post,
                           int Cmov, cudaStream_t st, bool* handled);
+int launch_modet_attn_tma2(const float* q, const float* k, const float* rpb, const float* ln_gamma, const float* ln_beta,
+                           const float* flow_in, const float* moving, float* w_out, float* flow_out, float* moved, int B,
+                           int D, int H, int W, float scale, float post, int Cmov, cudaStream_t st, bool* handled);
+
+// A/B knob: SMILE_FUSED_V1=1 runs the first-generation kernel (one voxel per thread, attn_tma.cu)
+static inline bool use_v1() {
+  static const bool v1 = [] { const char* e = getenv("SMILE_FUSED_V1"); return e != nullptr && e[0] == '1'; }();
+  return v1;
+}
 
 static inline int grid1d(long long n, int block) {
   long long g = ceil_div_ll(n, block);
@@ -184,7 +193,10 @@ int launch_modet_attn(const float* q, const float* k, const float* rpb, float* o
   const bool exact = attn_exact();
   if (heads == 1 && hd == 6 && !exact) {
     bool handled = false;
-    int rc = launch_modet_attn_tma(q, k, rpb, nullptr, nullptr, out, nullptr, nullptr, B, D, H, W, scale, 1.0f, 0, st, &handled);
+    int rc = use_v1() ? launch_modet_attn_tma(q, k, rpb, nullptr, nullptr, out, nullptr, nullptr, B, D, H, W, scale, 1.0f, 0,
+                                              st, &handled)
+                      : launch_modet_attn_tma2(q, k, rpb, nullptr, nullptr, nullptr, nullptr, out, nullptr, nullptr, B, D, H,
+                                               W, scale, 1.0f, 0, st, &handled);
     if (handled) return rc;
   }
   const long long total = (long long)D * H * W * heads;
@@ -205,13 +217,15 @@ int launch_modet_attn(const float* q, const float* k, const float* rpb, float* o
   return check_launch("modet_attn");
 }
 
-int launch_modet_fused(const float* q, const float* k, const float* rpb, const float* flow_in, const float* moving,
-                       float* flow_out, float* moved, int B, int D, int H, int W, int hd, float scale, float post,
-                       int Cmov, cudaStream_t st) {
+int launch_modet_fused(const float* q, const float* k, const float* rpb, const float* ln_gamma, const float* ln_beta,
+                       const float* flow_in, const float* moving, float* flow_out, float* moved, int B, int D, int H, int W,
+                       int hd, float scale, float post, int Cmov, cudaStream_t st) {
   if (hd == 6 && !attn_exact()) {
     bool handled = false;
-    int rc = launch_modet_attn_tma(q, k, rpb, flow_in, moving, nullptr, flow_out, moved, B, D, H, W, scale, post, Cmov, st,
-                                   &handled);
+    int rc = use_v1() ? launch_modet_attn_tma(q, k, rpb, flow_in, moving, nullptr, flow_out, moved, B, D, H, W, scale, post,
+                                              Cmov, st, &handled)
+                      : launch_modet_attn_tma2(q, k, rpb, ln_gamma, ln_beta, flow_in, moving, nullptr, flow_out, moved, B, D,
+                                               H, W, scale, post, Cmov, st, &handled);
     if (handled) return rc;
   }
   const long long N = (long long)D * H * W;

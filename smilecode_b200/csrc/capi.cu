@@ -91,10 +91,11 @@ int smile_flow_compose_fwd(const float* flow, const float* w, float* out, int B,
   return launch_compose(flow, w, out, B, D, H, W, postmul, (cudaStream_t)stream);
 }
 
-int smile_modet_fused_fwd(const float* q, const float* k, const float* rpb, const float* flow_in, const float* moving,
-                          float* flow_out, float* moved, int B, int D, int H, int W, int head_dim, float scale,
-                          float postmul, int Cmov, smile_stream_t stream) {
+int smile_modet_fused_fwd(const float* q, const float* k, const float* rpb, const float* ln_gamma, const float* ln_beta,
+                          const float* flow_in, const float* moving, float* flow_out, float* moved, int B, int D, int H,
+                          int W, int head_dim, float scale, float postmul, int Cmov, smile_stream_t stream) {
   REQUIRE_PTR(q);
+  REQUIRE((ln_gamma == nullptr) == (ln_beta == nullptr), "%s: ln_gamma and ln_beta must be given together", __func__);
   REQUIRE_PTR(k);
   REQUIRE_PTR(flow_in);
   REQUIRE_PTR(flow_out);
@@ -106,8 +107,8 @@ int smile_modet_fused_fwd(const float* q, const float* k, const float* rpb, cons
     REQUIRE_PTR(moving);
     REQUIRE(aligned16(moved) && Cmov > 0, "%s: moved misaligned or Cmov=%d", __func__, Cmov);
   }
-  return launch_modet_fused(q, k, rpb, flow_in, moving, flow_out, moved, B, D, H, W, head_dim, scale, postmul, Cmov,
-                            (cudaStream_t)stream);
+  return launch_modet_fused(q, k, rpb, ln_gamma, ln_beta, flow_in, moving, flow_out, moved, B, D, H, W, head_dim, scale,
+                            postmul, Cmov, (cudaStream_t)stream);
 }
 
 int smile_proj_ln_fwd(const float* feat, const float* weight, const float* bias, const float* gamma, const float* beta,

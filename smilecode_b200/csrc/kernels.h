@@ -16,9 +16,11 @@ int launch_upsample2x(const float* x, float* out, int B, int C, int D, int H, in
 int launch_modet_attn(const float* q, const float* k, const float* rpb, float* out, int B, int D, int H, int W,
                       int heads, int hd, float scale, cudaStream_t st);
 // fused heads==1 level: w = attn(q,k); flow_out = post*(T(flow_in, w) + w); optionally moved = T(moving, flow_out)
-int launch_modet_fused(const float* q, const float* k, const float* rpb, const float* flow_in, const float* moving,
-                       float* flow_out, float* moved, int B, int D, int H, int W, int hd, float scale, float post,
-                       int Cmov, cudaStream_t st);
+// ln_gamma / ln_beta: optional device pointers to the LayerNorm affine parameters that produced q and k (maximum-free
+// softmax when the logit bound they imply is small; null = always the online-maximum softmax)
+int launch_modet_fused(const float* q, const float* k, const float* rpb, const float* ln_gamma, const float* ln_beta,
+                       const float* flow_in, const float* moving, float* flow_out, float* moved, int B, int D, int H, int W,
+                       int hd, float scale, float post, int Cmov, cudaStream_t st);
 
 // proj.cu
 int launch_proj_ln(const float* feat, const float* weight, const float* bias, const float* gamma, const float* beta,

@@ -179,3 +179,67 @@ __device__ __forceinline__ float st_coord_fast(float idx, float f, float sm1, fl
 
 }  // namespace
 }  // namespace smile
+
+// ---------------------------------------------------------------------------------------------
+// Packed pairs kept in ONE 64-bit register (attn_tma2.cu).  With the float2 helpers above every call re-packs its
+// operands inside its own asm block, and ptxas materialises those packs as MOV / IMAD.MOV whenever the two halves do
+// not already sit in an aligned register pair (measured: 173 moves per thread-step in the first two-voxel kernel).
+// A p2 value is packed once (pk) and stays packed across uses.
+// ---------------------------------------------------------------------------------------------
+namespace smile {
+namespace {
+typedef unsigned long long p2;
+
+__device__ __forceinline__ p2 pk(float x, float y) {
+  p2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ float lo(p2 a) {
+  float x, y;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a));
+  return x;
+}
+__device__ __forceinline__ float hi(p2 a) {
+  float x, y;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a));
+  return y;
+}
+__device__ __forceinline__ p2 pfma(p2 a, p2 b, p2 c) {
+  p2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ p2 pfmas(p2 a, float b, p2 c) {   // scalar b broadcast to both lanes (SASS operand form R.F32)
+  p2 d;
+  asm("{\n\t.reg .b64 rb;\n\tmov.b64 rb, {%2, %2};\n\tfma.rn.f32x2 %0, %1, rb, %3;\n\t}" : "=l"(d) : "l"(a), "f"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ p2 pmul(p2 a, p2 b) {
+  p2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ p2 pmuls(p2 a, float b) {
+  p2 d;
+  asm("{\n\t.reg .b64 rb;\n\tmov.b64 rb, {%2, %2};\n\tmul.rn.f32x2 %0, %1, rb;\n\t}" : "=l"(d) : "l"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ p2 padd(p2 a, p2 b) {
+  p2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ p2 padds(p2 a, float b) {
+  p2 d;
+  asm("{\n\t.reg .b64 rb;\n\tmov.b64 rb, {%2, %2};\n\tadd.rn.f32x2 %0, %1, rb;\n\t}" : "=l"(d) : "l"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ p2 psub(p2 a, p2 b) {
+  p2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ p2 pex2(p2 a) { return pk(ex2(lo(a)), ex2(hi(a))); }
+}  // namespace
+}  // namespace smile

@@ -263,6 +263,16 @@ class ModeT(nn.Module):
         flow = ag.Warp.apply(flow, w) + w
         return ag.Warp.apply(moving, flow), flow
 
+    # The tensor-core convolutions keep prepared copies of their weights (ops._prepared_weights); every entry point
+    # through which weights are commonly replaced drops them.
+    def load_state_dict(self, *args, **kwargs):
+        ops.invalidate_prepared_weights()
+        return super().load_state_dict(*args, **kwargs)
+
+    def train(self, mode: bool = True):
+        ops.invalidate_prepared_weights()
+        return super().train(mode)
+
     def forward(self, moving, fixed):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             return self._forward_train(moving, fixed)
@@ -292,11 +302,11 @@ class ModeT(nn.Module):
         # level 2, 1: single head, attention + compose (+ final warp) fused (models.py:400-410)
         pb, mdt = self.projblock2, self.mdt2
         f2, _ = ops.modet_fused(pb(Fx[1]), pb.of_warped(M[1], flow), mdt.rpb if mdt.use_rpb else None, flow, None,
-                                mdt.scale, postmul=2.0)
+                                mdt.scale, postmul=2.0, ln_gamma=pb.norm.weight, ln_beta=pb.norm.bias)
         flow = ops.upsample2x(f2)
         pb, mdt = self.projblock1, self.mdt1
         flow, y_moved = ops.modet_fused(pb(Fx[0]), pb.of_warped(M[0], flow), mdt.rpb if mdt.use_rpb else None, flow,
-                                        moving, mdt.scale, postmul=1.0)
+                                        moving, mdt.scale, postmul=1.0, ln_gamma=pb.norm.weight, ln_beta=pb.norm.bias)
         return y_moved, flow
 
 

@@ -134,9 +134,12 @@ def flow_compose(flow: Tensor, w: Tensor, postmul: float = 1.0) -> Tensor:
 
 
 def modet_fused(q: Tensor, k: Tensor, rpb: Optional[Tensor], flow_in: Tensor, moving: Optional[Tensor], scale: float,
-                postmul: float = 1.0) -> Tuple[Tensor, Optional[Tensor]]:
+                postmul: float = 1.0, ln_gamma: Optional[Tensor] = None,
+                ln_beta: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
     """heads==1 level in one kernel (ModeT/models.py:401-403, 406-410):
-    w = mdt(q,k); flow_out = postmul*(T(flow_in,w)+w); moved = T(moving, flow_out) if moving is given."""
+    w = mdt(q,k); flow_out = postmul*(T(flow_in,w)+w); moved = T(moving, flow_out) if moving is given.
+    ln_gamma / ln_beta: the LayerNorm affine parameters of the ProjectionLayer that produced q AND k (both or neither);
+    they let the kernel bound the logits and skip the running maximum of the softmax (see include/smilecode_b200.h)."""
     q = _chk(q, "q", 5)
     k = _chk(k, "k", 5)
     flow_in = _chk(flow_in, "flow_in", 5)
@@ -147,6 +150,12 @@ def modet_fused(q: Tensor, k: Tensor, rpb: Optional[Tensor], flow_in: Tensor, mo
         rpb = _chk(rpb, "rpb", 4)
         if tuple(rpb.shape) != (1, 3, 3, 3):
             raise SmileError("modet_fused handles heads == 1 only (rpb must be [1,3,3,3])")
+    if (ln_gamma is None) != (ln_beta is None):
+        raise SmileError("modet_fused: ln_gamma and ln_beta must be given together")
+    if ln_gamma is not None:
+        ln_gamma, ln_beta = _chk(ln_gamma, "ln_gamma", 1), _chk(ln_beta, "ln_beta", 1)
+        if ln_gamma.numel() != hd or ln_beta.numel() != hd:
+            raise SmileError(f"modet_fused: ln_gamma / ln_beta must have head_dim={hd} elements")
     flow_out = torch.empty_like(flow_in)
     moved = None
     cm = 0
@@ -156,7 +165,7 @@ def modet_fused(q: Tensor, k: Tensor, rpb: Optional[Tensor], flow_in: Tensor, mo
         if tuple(moving.shape) != (B, cm, D, H, W):
             raise SmileError("modet_fused: moving must be [B,C,D,H,W] at the flow resolution")
         moved = torch.empty_like(moving)
-    call("smile_modet_fused_fwd", q.data_ptr(), k.data_ptr(), _ptr(rpb), flow_in.data_ptr(), _ptr(moving),
+    call("smile_modet_fused_fwd", q.data_ptr(), k.data_ptr(), _ptr(rpb), _ptr(ln_gamma), _ptr(ln_beta), flow_in.data_ptr(), _ptr(moving),
          flow_out.data_ptr(), _ptr(moved), B, D, H, W, hd, float(scale), float(postmul), cm, _stream(),
          label=f"[{D}x{H}x{W} mov{cm}]")
     return flow_out, moved
@@ -200,10 +209,21 @@ def warp_proj_ln(src: Tensor, flow: Tensor, weight: Tensor, bias: Tensor, gamma:
     return out
 
 
-# Split / re-arranged weights for the tensor-core convolution, prepared once per nn.Parameter and refreshed when the
-# parameter is updated in place (optimizer step -> version counter) or re-allocated.  Plain tensors (e.g. the flipped
-# weights of the data-gradient pass) are not cached: the library prepares them per call.
+# Split / re-arranged weights for the tensor-core convolution, prepared once per nn.Parameter and refreshed when torch can
+# see that the parameter changed: an in-place update through the autograd-tracked tensor (optimizer step, `p.copy_()`,
+# `load_state_dict` -> version counter), a re-allocation (`.to()`, `.cuda()` -> data_ptr) or a new Parameter object.
+# What torch canNOT see is a write through `p.data` (`p.data.copy_()`, `p.data.mul_()`: EMA / SWA loops, some custom
+# initialisers) or through a raw pointer (our own fused Adam clears the cache itself): call
+# `ops.invalidate_prepared_weights()` after such a write, or set `ops.PREPARED_WEIGHT_CACHE = False` to prepare the
+# weights on every call (~1 % of a forward).  `ModeT.load_state_dict`, `.train()` and `.eval()` invalidate as well.
+# Plain tensors (e.g. the flipped weights of the data-gradient pass) are never cached.
 _WPREP_CACHE: dict = {}
+PREPARED_WEIGHT_CACHE = True
+
+
+def invalidate_prepared_weights() -> None:
+    """Forget every prepared (split / re-arranged) tensor-core weight block; the next conv3d call prepares them again."""
+    _WPREP_CACHE.clear()
 
 
 def _prepared_weights(weight: Tensor, Cin: int, Cout: int) -> Optional[Tensor]:
@@ -211,17 +231,23 @@ def _prepared_weights(weight: Tensor, Cin: int, Cout: int) -> Optional[Tensor]:
     # which torch's version counter does not see
     if torch.is_grad_enabled() or not isinstance(weight, torch.nn.Parameter) or Cin < 16 or Cout < 12:
         return None
-    key = id(weight)
-    hit = _WPREP_CACHE.get(key)
-    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
-        return hit[3]
     import weakref
     from ._lib import lib
+    key = id(weight)
+    cur = torch.cuda.current_stream(weight.device)
+    hit = _WPREP_CACHE.get(key) if PREPARED_WEIGHT_CACHE else None
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
+        if hit[5] != cur.cuda_stream:          # prepared on another stream: order this stream after the preparation
+            cur.wait_event(hit[4])
+        return hit[3]
     n = int(lib().smile_conv3d_tc_prep_floats(Cin, Cout))
     wprep = torch.empty(n, device=weight.device, dtype=torch.float32)
     call("smile_conv3d_tc_prep", weight.data_ptr(), wprep.data_ptr(), Cin, Cout, _stream())
-    _WPREP_CACHE[key] = (weakref.ref(weight, lambda _r, k=key: _WPREP_CACHE.pop(k, None)), weight._version,
-                         weight.data_ptr(), wprep)
+    if PREPARED_WEIGHT_CACHE:
+        done = torch.cuda.Event()
+        done.record(cur)
+        _WPREP_CACHE[key] = (weakref.ref(weight, lambda _r, k=key: _WPREP_CACHE.pop(k, None)), weight._version,
+                             weight.data_ptr(), wprep, done, cur.cuda_stream)
     return wprep
 
 

@@ -25,6 +25,18 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     return begin, begin + base + (1 if rank < extra else 0)
 
 
+def flat_layout(params: Iterable[torch.nn.Parameter], align: int = 4) -> Tuple[List[int], int]:
+    """Offsets (in elements) of `params` packed into one flat buffer with every parameter starting on a multiple of `align`
+    elements (4 fp32 = 16 bytes: the C ABI's pointer alignment -- an unaligned view would be cloned on every kernel call),
+    and the padded total.  The parameter buffer of `train.Trainer` and the gradient bucket below share this layout, so the
+    fused Adam update runs over one contiguous range; the padding stays zero."""
+    offs, off = [], 0
+    for p in params:
+        offs.append(off)
+        off += (p.numel() + align - 1) // align * align
+    return offs, off
+
+
 class FlatGradAllReduce:
     """Averages the gradients of `params` across ranks with ONE all-reduce over a flat fp32 bucket.
 
@@ -36,18 +48,16 @@ class FlatGradAllReduce:
         if not self.params:
             raise ValueError("no trainable parameters")
         dev, dt = self.params[0].device, torch.float32
-        self.numel = sum(p.numel() for p in self.params)
+        offs, self.numel = flat_layout(self.params)
         self.bucket = torch.zeros(self.numel, device=dev, dtype=dt)
         self.group = group
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, offs):
             if p.dtype != dt or p.device != dev:
                 raise ValueError("FlatGradAllReduce expects fp32 parameters on one device")
             view = self.bucket[off:off + p.numel()].view_as(p)
             if p.grad is not None:
                 view.copy_(p.grad)
             p.grad = view
-            off += p.numel()
 
     def zero_(self) -> None:
         self.bucket.zero_()

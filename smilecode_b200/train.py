@@ -10,7 +10,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import losses, ops
-from .parallel import FlatGradAllReduce
+from .parallel import FlatGradAllReduce, flat_layout
 
 
 class Trainer:
@@ -23,14 +23,13 @@ class Trainer:
         self.params = [p for p in model.parameters() if p.requires_grad]
         dev = self.params[0].device
         # flat parameter / gradient / optimizer-state buffers: parameters become views into `flat`
-        self.numel = sum(p.numel() for p in self.params)
-        self.flat = torch.empty(self.numel, device=dev, dtype=torch.float32)
-        off = 0
-        for p in self.params:
+        # (16-byte aligned starts, zero padding: parallel.flat_layout -- the gradient bucket uses the same offsets)
+        offs, self.numel = flat_layout(self.params)
+        self.flat = torch.zeros(self.numel, device=dev, dtype=torch.float32)
+        for p, off in zip(self.params, offs):
             view = self.flat[off:off + p.numel()].view_as(p)
             view.copy_(p.data)
             p.data = view
-            off += p.numel()
         self.sync = FlatGradAllReduce(self.params)          # .grad tensors become views into sync.bucket
         self.distributed = bool(distributed)
         self.exp_avg = torch.zeros_like(self.flat)

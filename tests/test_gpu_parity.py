@@ -229,6 +229,27 @@ def test_conv_prepared_weight_cache(ops):
         w.mul_(-2.0)                                              # in-place update bumps the version counter
         upd, _ = ops.conv3d(x, w, b)
         assert rel_err(upd.cpu(), orc.conv3(x.cpu(), w.detach().cpu(), b.cpu())) <= 2e-6
+        # a write through .data is invisible to torch: documented contract = invalidate explicitly
+        w.data.mul_(0.5)
+        ops.invalidate_prepared_weights()
+        upd, _ = ops.conv3d(x, w, b)
+        assert rel_err(upd.cpu(), orc.conv3(x.cpu(), w.detach().cpu(), b.cpu())) <= 2e-6
+        # ... or switch the cache off
+        ops.PREPARED_WEIGHT_CACHE = False
+        try:
+            w.data.mul_(3.0)
+            upd, _ = ops.conv3d(x, w, b)
+            assert rel_err(upd.cpu(), orc.conv3(x.cpu(), w.detach().cpu(), b.cpu())) <= 2e-6
+        finally:
+            ops.PREPARED_WEIGHT_CACHE = True
+        # consumed on another stream than the one that prepared it: ordered by an event
+        side = torch.cuda.Stream()
+        w.mul_(1.5)
+        with torch.cuda.stream(side):
+            a1, _ = ops.conv3d(x, w, b)
+        b1, _ = ops.conv3d(x, w, b)
+        torch.cuda.synchronize()
+        assert torch.equal(a1, b1)
 
 
 @pytest.mark.parametrize("name", golden_names("cwm_"))
@@ -264,25 +285,50 @@ def test_encoder_golden():
 def test_fused_matches_unfused(ops, shape, sharp):
     """Covers the TMA-staged marching kernel (W % 4 == 0: partial tiles in H and W, several depth
     segments per CTA, batch > 1, saturated softmax -> |w| == 1 -> out-of-window gather path) and the
-    generic fused kernel (other W)."""
+    generic fused kernel (other W).  q, k are real LayerNorm outputs; the kernel is called without the LayerNorm
+    parameters (online-maximum softmax) and with them (maximum-free softmax when the bound they imply is small; with
+    sharp = 40 the bound is ~800 and the kernel must fall back to the online maximum by itself)."""
     B, D, H, W = shape
     g = torch.Generator().manual_seed(10)
-    q = torch.randn(B, D, H, W, 6, generator=g) * sharp
-    k = torch.randn(B, D, H, W, 6, generator=g)
+    gamma = (torch.rand(6, generator=g) + 0.5) * sharp ** 0.5
+    beta = torch.randn(6, generator=g) * 0.1
+    ln = lambda t: torch.nn.functional.layer_norm(t, (6,)) * gamma + beta
+    q = ln(torch.randn(B, D, H, W, 6, generator=g))
+    k = ln(torch.randn(B, D, H, W, 6, generator=g))
     rpb = torch.randn(1, 3, 3, 3, generator=g) * 0.5
     # white-noise fields have O(1) voxel-to-voxel jumps, so the ~1e-6 error of w (approximate exp2)
     # is amplified by the sampled field's gradient; 1e-4 is the contract, typical error is 2e-5
     flow = torch.randn(B, 3, D, H, W, generator=g) * 2
     mov = torch.rand(B, 1, D, H, W, generator=g)
     w = orc.modet_attention(q, k, rpb, 1, 1.0)
+    if sharp > 1:
+        assert float(w.abs().max()) > 0.999           # the saturated case really saturates
     for post in (1.0, 2.0):
         f_ref = post * (orc.warp_trilinear(flow, w) + w)
         m_ref = orc.warp_trilinear(mov, f_ref)
-        f, m = ops.modet_fused(dev(q), dev(k), dev(rpb), dev(flow), dev(mov), 1.0, post)
-        assert rel_err(f.cpu(), f_ref) <= 1e-4          # north_star: 1e-4 relative fp32 (|f| reaches ~10 here)
-        assert (m.cpu() - m_ref).abs().max() <= 1e-4
-        f_only, none = ops.modet_fused(dev(q), dev(k), dev(rpb), dev(flow), None, 1.0, post)
-        assert none is None and torch.equal(f_only, f)
+        for lnp in ({}, {"ln_gamma": dev(gamma), "ln_beta": dev(beta)}):
+            f, m = ops.modet_fused(dev(q), dev(k), dev(rpb), dev(flow), dev(mov), 1.0, post, **lnp)
+            assert rel_err(f.cpu(), f_ref) <= 1e-4          # north_star: 1e-4 relative fp32 (|f| reaches ~10 here)
+            assert (m.cpu() - m_ref).abs().max() <= 1e-4
+            f_only, none = ops.modet_fused(dev(q), dev(k), dev(rpb), dev(flow), None, 1.0, post, **lnp)
+            assert none is None and torch.equal(f_only, f)
+
+
+def test_fused_ln_promise_is_validated(ops):
+    """ln_gamma / ln_beta must come together and have head_dim elements; huge or non-finite parameters select the safe path
+    (finite output), they do not poison the result."""
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(1, 4, 8, 32, 6, generator=g)
+    k = torch.randn(1, 4, 8, 32, 6, generator=g)
+    flow = torch.randn(1, 3, 4, 8, 32, generator=g)
+    with pytest.raises(Exception):
+        ops.modet_fused(dev(q), dev(k), None, dev(flow), None, 1.0, 1.0, ln_gamma=dev(torch.ones(6)))
+    with pytest.raises(Exception):
+        ops.modet_fused(dev(q), dev(k), None, dev(flow), None, 1.0, 1.0, ln_gamma=dev(torch.ones(5)), ln_beta=dev(torch.zeros(5)))
+    ref, _ = ops.modet_fused(dev(q), dev(k), None, dev(flow), None, 1.0, 1.0)
+    for gam in (torch.full((6,), 1e4), torch.full((6,), float("nan"))):
+        out, _ = ops.modet_fused(dev(q), dev(k), None, dev(flow), None, 1.0, 1.0, ln_gamma=dev(gam), ln_beta=dev(torch.zeros(6)))
+        assert torch.equal(out, ref)
 
 
 # ------------------------------------------------------------------ a9 end to end
@@ -431,18 +477,43 @@ def test_warp_proj_ln_matches_unfused_oracle(ops, cin, c, shape):
 
 # ------------------------------------------------------------------ host-to-host pipeline
 def test_registration_pipeline_matches_direct_calls():
-    from smilecode_b200 import models
+    from smilecode_b200 import metrics, models
     from smilecode_b200.pipeline import RegistrationPipeline
     from smilecode_b200.synth import make_pair, randomize_weights
     shape = (16, 32, 32)
     model = models.ModeT(shape, head_dim=6, num_heads=[8, 4, 2, 1, 1], scale=1)
     randomize_weights(model, seed=7)
     model = model.cuda().eval()
-    pairs = [tuple(t.pin_memory() for t in make_pair(shape, batch=1, seed=50 + i)) for i in range(5)]
-    pipe = RegistrationPipeline(model, shape, depth=2)
+    pairs = [tuple(t.pin_memory() for t in make_pair(shape, batch=1, seed=50 + i)) for i in range(9)]
+    with torch.no_grad():
+        direct = [tuple(t.cpu() for t in model(mv.cuda(), fx.cuda())) for mv, fx in pairs]
+    # both outputs, results cloned at once
+    pipe = RegistrationPipeline(model, shape, depth=2, outputs=("moved", "flow"))
     outs = [(m.clone(), f.clone()) for m, f in pipe.run(pairs)]
     assert len(outs) == len(pairs)
+    for (moved, flow), (moved_h, flow_h) in zip(direct, outs):
+        assert torch.equal(moved, moved_h) and torch.equal(flow, flow_h)
+    # default: flow only; a result stays valid while `depth` further results are requested (it used to be
+    # overwritten after one) -- hold every buffer for `depth` more next() calls before looking at it
+    for depth in (1, 2, 3):
+        pipe = RegistrationPipeline(model, shape, depth=depth)
+        assert pipe.d2h_bytes == 3 * 16 * 32 * 32 * 4
+        held, seen = [], 0
+        for flow_h in pipe.run(pairs):
+            held.append(flow_h)
+            if len(held) > depth:
+                torch.cuda.synchronize()               # let every enqueued copy land: a too-early overwrite would show
+                assert torch.equal(held.pop(0), direct[seen][1])
+                seen += 1
+        for h in held:
+            assert torch.equal(h, direct[seen][1])
+            seen += 1
+        assert seen == len(pairs)
+    # metrics-only: nothing but the reduced numbers leaves the device
+    pipe = RegistrationPipeline(model, shape, depth=2, outputs=(),
+                                reduce=lambda moved, flow, extra: metrics.jacobian_determinant_vxm(flow, want_det=False)[1])
+    assert pipe.d2h_bytes == 0
+    fracs = [int(r) for r in pipe.run(pairs)]
     with torch.no_grad():
-        for (mv, fx), (moved_h, flow_h) in zip(pairs, outs):
-            moved, flow = model(mv.cuda(), fx.cuda())
-            assert torch.equal(moved.cpu(), moved_h) and torch.equal(flow.cpu(), flow_h)
+        want = [int(metrics.jacobian_determinant_vxm(f.cuda(), want_det=False)[1]) for _, f in direct]
+    assert fracs == want

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from smilecode_b200.parallel import FlatGradAllReduce, shard_range
+from smilecode_b200.parallel import FlatGradAllReduce, flat_layout, shard_range
 
 
 def test_shard_range_partitions_exactly():
@@ -38,7 +38,8 @@ def _worker(rank, world, port, out):
     net(x[b:e]).pow(2).sum().backward()                     # sum-loss: mean over ranks == global grad / world
     assert all(p.grad.data_ptr() >= sync.bucket.data_ptr() for p in net.parameters())   # grads live in the bucket
     sync.allreduce_mean_()
-    flat = sync.bucket.clone()
+    assert all(p.grad.data_ptr() % 16 == 0 for p in net.parameters())                   # every view is 16-byte aligned
+    flat = torch.cat([p.grad.flatten() for p in net.parameters()])
     # single-process reference on the whole batch
     ref = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
     ref.load_state_dict(net.state_dict())
@@ -54,3 +55,10 @@ def test_flat_grad_allreduce_equals_single_process_gradient():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert len(out) == world and max(out.values()) < 1e-6, dict(out)
+
+
+def test_flat_layout_pads_to_16_bytes():
+    ps = [torch.nn.Parameter(torch.zeros(n)) for n in (6, 27, 4, 1, 128)]
+    offs, total = flat_layout(ps)
+    assert offs == [0, 8, 36, 40, 44] and total == 172
+    assert all(o % 4 == 0 for o in offs)

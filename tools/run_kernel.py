@@ -33,7 +33,13 @@ if what in ("fused", "fused_l2", "fused_nomov"):
     rpb = torch.randn(1, 3, 3, 3, device=dev, generator=g) * 0.5
     flow = smooth_flow(shp, 2.0)
     mov = torch.rand(1, 1, *shp, device=dev, generator=g) if what == "fused" else None
-    fn = lambda: ops.modet_fused(q, k, rpb, flow, mov, 1.0, 1.0 if what == "fused" else 2.0)
+    import os
+    lnp = {}
+    if os.environ.get("SMILE_RUN_LN", "1") == "1":      # q, k ~ N(0,1) per channel: |q|_2 <= 6 is NOT guaranteed for raw randn,
+        q = torch.nn.functional.layer_norm(q, (6,))     # so make them real LayerNorm outputs (gamma = 1, beta = 0)
+        k = torch.nn.functional.layer_norm(k, (6,))
+        lnp = {"ln_gamma": torch.ones(6, device=dev), "ln_beta": torch.zeros(6, device=dev)}
+    fn = lambda: ops.modet_fused(q, k, rpb, flow, mov, 1.0, 1.0 if what == "fused" else 2.0, **lnp)
     nbytes = (80 if what == "fused" else 72) * shp[0] * shp[1] * shp[2]
     if what == "fused_nomov":
         ops.modet_attention(q, k, rpb, 1, 1.0)

@@ -75,8 +75,9 @@ struct Cfg2 {
 struct Dims2 {
   int B, D, H, W;
   int ncol_h, ncol_w;
-  long long total_units;
-  int units_per_cta;
+  long long total_units;   // (row band, plane) units: B * ncol_h * D
+  int units_per_cta;       // ... per CTA group
+  int group;               // CTAs per group = ncol_w: the W-neighbour columns of a row band march in lockstep
   float dm1, hm1, wm1;
   float rd, rh, rw;
 };
@@ -605,20 +606,24 @@ fused_march2_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
   const int D = dm.D;
 
   if (tid == 0) {
-    const long long u_begin = (long long)blockIdx.x * dm.units_per_cta;
+    // CTA (g, m): group g owns a contiguous range of (row band, plane) units, member m takes column m of every band in
+    // it.  The ncol_w members of a group therefore read W-adjacent boxes of the same planes at the same time, and the
+    // 128-byte lines their halos share (a 160-byte flow row spans three) come from DRAM once and from L2 afterwards
+    // (measured: 492 -> see profiles/r03*_fused_v2_full.txt MB read per launch).
+    const int g = blockIdx.x / dm.group, m = blockIdx.x - g * dm.group;
+    const long long u_begin = (long long)g * dm.units_per_cta;
     long long u_end = u_begin + dm.units_per_cta;
     if (u_end > dm.total_units) u_end = dm.total_units;
     int ns = 0, stage = 0;
     long long u = u_begin;
     while (u < u_end && ns < MAXSEG) {
-      const long long col = u / D;
+      const long long band = u / D;
       Seg sg;
-      sg.d_a = (int)(u - col * D);
+      sg.d_a = (int)(u - band * D);
       sg.L = (int)((u_end - u) < (long long)(D - sg.d_a) ? (u_end - u) : (long long)(D - sg.d_a));
-      sg.w0 = (int)(col % dm.ncol_w) * TW;
-      const long long t2 = col / dm.ncol_w;
-      sg.h0 = (int)(t2 % dm.ncol_h) * C::ROWS;
-      sg.b = (int)(t2 / dm.ncol_h);
+      sg.w0 = m * TW;
+      sg.h0 = (int)(band % dm.ncol_h) * C::ROWS;
+      sg.b = (int)(band / dm.ncol_h);
       sg.s_begin = stage;
       segs[ns++] = sg;
       stage += sg.L + 2;
@@ -693,11 +698,16 @@ PFN_cuTensorMapEncodeTiled get_encode2() {
   return fn;
 }
 
+// L2 promotion of the halo boxes: their rows start 16 B (flow) / 48 B (keys) before a 128-byte boundary, so with 128-byte
+// promotion a 160-byte flow row pulls three 128-byte lines (measured: 492 MB read for 315 MB algorithmic).  SMILE_TMA_PROMO
+// = 0 none / 1 64 B / 2 128 B / 3 256 B overrides the default for experiments.
 bool encode4b(CUtensorMap* map, const void* base, const cuuint64_t (&dims)[4], const cuuint64_t (&strides)[3],
-              const cuuint32_t (&box)[4]) {
+              const cuuint32_t (&box)[4], CUtensorMapL2promotion promo) {
+  static const int knob = [] { const char* e = getenv("SMILE_TMA_PROMO"); return e ? atoi(e) : -1; }();
+  if (knob >= 0 && knob <= 3) promo = (CUtensorMapL2promotion)knob;
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult rc = get_encode2()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
     set_error("modet_fused(TMA v2): cuTensorMapEncodeTiled failed with CUresult %d", (int)rc);
@@ -732,12 +742,15 @@ int launch_tiles2(const float* q, const float* k, const float* rpb, const float*
   dm.B = B; dm.D = D; dm.H = H; dm.W = W;
   dm.ncol_h = ceil_div(H, C::ROWS);
   dm.ncol_w = ceil_div(W, TW);
-  dm.total_units = (long long)B * dm.ncol_h * dm.ncol_w * D;
-  long long per = ceil_div_ll(dm.total_units, (long long)kNumSMs);
+  dm.group = dm.ncol_w;
+  dm.total_units = (long long)B * dm.ncol_h * D;
+  int groups = kNumSMs / dm.group;                      // one CTA per SM: all groups are co-resident
+  if (groups < 1) groups = 1;                           // very wide volumes: more than one wave (still correct)
+  long long per = ceil_div_ll(dm.total_units, (long long)groups);
   if (per < 4) per = 4;
   if (per > (long long)(MAXSEG - 2) * D) per = (long long)(MAXSEG - 2) * D;
   dm.units_per_cta = (int)per;
-  const int grid = (int)ceil_div_ll(dm.total_units, per);
+  const int grid = (int)ceil_div_ll(dm.total_units, per) * dm.group;
   dm.dm1 = (float)(D - 1); dm.hm1 = (float)(H - 1); dm.wm1 = (float)(W - 1);
   dm.rd = 1.0f / dm.dm1; dm.rh = 1.0f / dm.hm1; dm.rw = 1.0f / dm.wm1;
 
@@ -746,12 +759,14 @@ int launch_tiles2(const float* q, const float* k, const float* rpb, const float*
   const cuuint64_t qk_str[3] = {(cuuint64_t)W * HD * 4, (cuuint64_t)H * W * HD * 4, (cuuint64_t)D * H * W * HD * 4};
   const cuuint32_t k_box[4] = {KW * HD, (cuuint32_t)C::KROWS, 1, 1};
   const cuuint32_t q_box[4] = {TW * HD, (cuuint32_t)C::ROWS, 1, 1};
-  if (!encode4b(&mk, k, qk_dims, qk_str, k_box) || !encode4b(&mq, q, qk_dims, qk_str, q_box)) return SMILE_ERR_CUDA;
+  if (!encode4b(&mk, k, qk_dims, qk_str, k_box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B) ||
+      !encode4b(&mq, q, qk_dims, qk_str, q_box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
+    return SMILE_ERR_CUDA;
   if (compose) {
     const cuuint64_t f_dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B * 3};
     const cuuint64_t f_str[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)D * H * W * 4};
     const cuuint32_t f_box[4] = {FWP, (cuuint32_t)C::KROWS, 1, 3};
-    if (!encode4b(&mf, flow_in, f_dims, f_str, f_box)) return SMILE_ERR_CUDA;
+    if (!encode4b(&mf, flow_in, f_dims, f_str, f_box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return SMILE_ERR_CUDA;
   } else {
     mf = mq;
   }

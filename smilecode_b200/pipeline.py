@@ -47,6 +47,7 @@ class RegistrationPipeline:
         self.nhost = 2 * self.depth
         chans = {"moved": 1, "flow": 3}
         self.out_h = [{o: pin(chans[o]) for o in self.outputs} for _ in range(self.nhost)]
+        self.red_h: List[Optional[torch.Tensor]] = [None] * self.nhost     # pinned landing buffers of `reduce` results
         ev = lambda n: [torch.cuda.Event() for _ in range(n)]
         self.in_ready, self.comp_done = ev(self.depth), ev(self.depth)
         self.out_done = ev(self.nhost)
@@ -83,6 +84,12 @@ class RegistrationPipeline:
                     if name in self.out_h[hs]:
                         self.out_h[hs][name].copy_(src, non_blocking=True)
                         src.record_stream(self.s_out)
+                if isinstance(red, torch.Tensor):      # device result of `reduce`: same asynchronous route to the host
+                    if self.red_h[hs] is None or self.red_h[hs].shape != red.shape or self.red_h[hs].dtype != red.dtype:
+                        self.red_h[hs] = torch.empty(red.shape, dtype=red.dtype).pin_memory()
+                    self.red_h[hs].copy_(red, non_blocking=True)
+                    red.record_stream(self.s_out)
+                    red = self.red_h[hs]
                 self.out_done[hs].record(self.s_out)
             pending.append((hs, red))
         while pending:
@@ -92,6 +99,5 @@ class RegistrationPipeline:
         self.out_done[hs].synchronize()
         outs = tuple(self.out_h[hs][o] for o in self.outputs)
         if self.reduce is not None:
-            red = red.cpu() if isinstance(red, torch.Tensor) else red
             return (*outs, red) if outs else red
         return outs[0] if len(outs) == 1 else outs

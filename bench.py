@@ -241,6 +241,9 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
     ap.add_argument("--config", default="lpba", choices=sorted(CONFIGS))
     ap.add_argument("--train-batch", type=int, default=1, help="pairs per GPU in the training-step leg")
+    ap.add_argument("--train-dtype", default="fp32", choices=["fp32", "bf16"],
+                    help="bf16: Conv3d forward and data-gradient products on bf16 tensor cores, fp32 accumulation "
+                         "(BASELINE.json configs[2..3]); everything else fp32")
     ap.add_argument("--comparators", action="store_true",
                     help="also time the staged reference on this GPU (PyTorch eager, and ModeT-cu with its own extension)")
     args = ap.parse_args()
@@ -420,6 +423,25 @@ def main():
                        "note": "not the headline: BASELINE configs[1] is one pair per forward"}
             del mb, fb
 
+        # ---------------- informational: the same forward with the convolutions on bf16 tensor cores
+        bf16_fwd = None
+        if rank == 0 and world == 1:
+            model.conv_precision = "bf16"
+            for _ in range(2):
+                _, flow_b = model(moving, fixed)
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record(stream)
+            for _ in range(5):
+                _, flow_b = model(moving, fixed)
+            b1.record(stream)
+            torch.cuda.synchronize()
+            model.conv_precision = "fp32"
+            bms = b0.elapsed_time(b1) / 5
+            bf16_fwd = {"value": 1e3 / bms, "unit": UNIT, "ms_per_step": bms,
+                        "max_abs_flow_diff_vs_fp32_path": float((flow_b - flow).abs().max()),
+                        "note": "conv_precision='bf16': Conv3d products on tcgen05 kind::f16; not the headline (fp32 is the reference's dtype)"}
+            del flow_b
+
         breakdown = None
         if args.breakdown or rank == 0:
             _lib.profile_start()
@@ -440,6 +462,7 @@ def main():
         tmodel = models.ModeT(SHAPE, head_dim=6, num_heads=HEADS, scale=1)
         randomize_weights(tmodel, seed=1234)
         tmodel = tmodel.to(dev)
+        tmodel.conv_precision = args.train_dtype
         trainer = Trainer(tmodel, lr=1e-4, distributed=world > 1)
         TB = max(1, args.train_batch)
         if TB > 1:
@@ -458,9 +481,10 @@ def main():
         barrier()
         tms = reduce_max(t0.elapsed_time(t1)) / TK
         train = {"value": world * TB * 1e3 / tms, "unit": "pairs/s", "ms_per_step": tms, "steps": TK,
-                 "pairs_per_gpu_per_step": TB, "global_pairs_per_step": TB * world, "dtype": "f32",
+                 "pairs_per_gpu_per_step": TB, "global_pairs_per_step": TB * world,
+                 "dtype": "f32" if args.train_dtype == "fp32" else "bf16 conv MMA operands (tcgen05 kind::f16), f32 accumulation / activations / everything else",
                  "gpu_launches_per_step": (_lib.LAUNCHES - l0) // TK, "loss": float(tloss),
-                 "config": f"fp32 training step, {TB} pair(s) per GPU, NCC_vxm(9) + Grad3d(l2), Adam(amsgrad); "
+                 "config": f"{args.train_dtype} training step, {TB} pair(s) per GPU, NCC_vxm(9) + Grad3d(l2), Adam(amsgrad); "
                            + ("flat-bucket NCCL gradient all-reduce" if world > 1 else "single GPU, no collective")}
         del trainer, tmodel
         torch.cuda.empty_cache()
@@ -502,7 +526,7 @@ def main():
                         "ms_per_step": e2e_ms_step,
                         "what": "RegistrationPipeline(outputs=('flow',)): pair up from pinned host memory, flow down into "
                                 "pinned host memory (what infer.py:79-89 moves per pair)", "other_modes": e2e_modes},
-                "step_ms_min_max": [min(step_ms), max(step_ms)], "gpu_launches": launches, "gpu_launches_per_step": launches // K, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "train": train, "batched": batched,
+                "step_ms_min_max": [min(step_ms), max(step_ms)], "gpu_launches": launches, "gpu_launches_per_step": launches // K, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "train": train, "batched": batched, "bf16_forward": bf16_fwd,
                 "comparators": comparators}
         if breakdown:
             line["kernel_ms"] = {name: round(ms, 4) for ms, _, name in breakdown[:12]}

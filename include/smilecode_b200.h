@@ -100,6 +100,15 @@ int smile_conv3d_fwd(const float* in, const float* weight, const float* bias, fl
                      double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
                      smile_stream_t stream);
 
+/* Same contract with bf16 MMA operands: tcgen05 kind::f16, fp32 accumulation in TMEM (csrc/conv_bf16.cu) -- the
+ * reduced-precision encoder of BASELINE.json configs[2..3].  in / out / statistics stay fp32; only the operands of the
+ * products are rounded (activations after the normalise-on-load, weights), so a layer output differs from
+ * smile_conv3d_fwd by ~1e-3 relative.  Layers with fewer than 4 input channels (and rows too wide for the staged halo)
+ * run on the fp32 kernels inside this call. */
+int smile_conv3d_bf16_fwd(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
+                          double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
+                          smile_stream_t stream);
+
 /* Optional prepared weights for the tensor-core convolution (layers with >= 16 input and >= 12 output channels on
  * volumes up to 48 voxels wide run on tcgen05 with a 3xTF32 split, csrc/conv_tc.cu).  smile_conv3d_fwd prepares the
  * split weights on every call into stream-ordered scratch; a caller with constant weights can do it once:

@@ -22,6 +22,7 @@ SIGNATURES = {
     "smile_proj_ln_fwd": [P, P, P, P, P, P, c_int, c_int, c_int, c_longlong, c_float, P],
     "smile_warp_proj_ln_fwd": [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P],
     "smile_conv3d_fwd": [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P],
+    "smile_conv3d_bf16_fwd": [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P],
     "smile_instnorm_lrelu_pool_fwd": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P],
     "smile_cwm_fuse_fwd": [P, P, P, c_int, c_int, c_longlong, P],
     "smile_modet_qkrpb_fwd": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],

@@ -102,6 +102,7 @@ class ConvINLReLU(Function):
         act, pooled = ops.instnorm_lrelu_pool(raw, stats, pool=bool(pool), inplace=True)
         ctx.save_for_backward(x, weight, act, stats)
         ctx.pool = bool(pool)
+        ctx.prec = ops.current_conv_precision()      # the data-gradient pass runs at the forward's precision
         if pool:
             return act, pooled
         return act
@@ -114,7 +115,8 @@ class ConvINLReLU(Function):
             g = g.clone() if g is not None else torch.zeros_like(act)
             ops.avgpool2_bwd_add(_c(g_pooled), g)
         d_raw = ops.in_lrelu_bwd(g, act, stats, mode=0)
-        dx, dw, db = ops.conv3d_bwd(d_raw, x, weight, need_x=ctx.needs_input_grad[0])
+        with ops.conv_precision(ctx.prec):
+            dx, dw, db = ops.conv3d_bwd(d_raw, x, weight, need_x=ctx.needs_input_grad[0])
         return dx, dw, db, None
 
 
@@ -126,13 +128,15 @@ class ConvLReLU(Function):
         x, weight, bias = _c(x), _c(weight), _c(bias)
         act, _ = ops.conv3d(x, weight, bias, act_out=True)
         ctx.save_for_backward(x, weight, act)
+        ctx.prec = ops.current_conv_precision()
         return act
 
     @staticmethod
     def backward(ctx, g):
         x, weight, act = ctx.saved_tensors
         d_raw = ops.in_lrelu_bwd(_c(g), act, None, mode=1)
-        dx, dw, db = ops.conv3d_bwd(d_raw, x, weight, need_x=ctx.needs_input_grad[0])
+        with ops.conv_precision(ctx.prec):
+            dx, dw, db = ops.conv3d_bwd(d_raw, x, weight, need_x=ctx.needs_input_grad[0])
         return dx, dw, db
 
 
@@ -143,12 +147,14 @@ class Conv(Function):
     def forward(ctx, x, weight, bias):
         x, weight, bias = _c(x), _c(weight), _c(bias)
         ctx.save_for_backward(x, weight)
+        ctx.prec = ops.current_conv_precision()
         return ops.conv3d(x, weight, bias)[0]
 
     @staticmethod
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
-        dx, dw, db = ops.conv3d_bwd(_c(g), x, weight, need_x=ctx.needs_input_grad[0])
+        with ops.conv_precision(ctx.prec):
+            dx, dw, db = ops.conv3d_bwd(_c(g), x, weight, need_x=ctx.needs_input_grad[0])
         return dx, dw, db
 
 

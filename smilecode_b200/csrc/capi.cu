@@ -160,6 +160,26 @@ int smile_conv3d_fwd(const float* in, const float* weight, const float* bias, fl
                        (cudaStream_t)stream);
 }
 
+int smile_conv3d_bf16_fwd(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
+                          double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
+                          smile_stream_t stream) {
+  REQUIRE_PTR(in);
+  REQUIRE_PTR(weight);
+  REQUIRE_PTR(bias);
+  REQUIRE_PTR(out);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(Cin > 0 && Cout > 0 && Cin <= 4096 && Cout <= 4096, "%s: Cin=%d Cout=%d out of range", __func__, Cin, Cout);
+  REQUIRE(in != out, "%s: out must not alias in", __func__);
+  REQUIRE((long long)B <= 65535, "%s: B=%d exceeds grid.z", __func__, B);
+  bool handled = false;
+  const int rc = launch_conv3d_bf16(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps,
+                                    (cudaStream_t)stream, &handled);
+  if (handled) return rc;
+  // shapes the bf16 tensor-core kernel does not take (one input channel, very wide rows) run at full precision
+  return launch_conv3d(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps,
+                       (cudaStream_t)stream);
+}
+
 long long smile_conv3d_tc_prep_floats(int Cin, int Cout) {
   if (Cin <= 0 || Cout <= 0 || Cin > 4096 || Cout > 4096) return 0;
   return conv3d_tc_prep_floats(Cin, Cout);

@@ -217,6 +217,9 @@ class ModeT(nn.Module):
         self.channels = channels
         self.step = 7
         self.inshape = inshape
+        # "fp32" (reference numerics) or "bf16": Conv3d products on bf16 tensor cores with fp32 accumulation
+        # (BASELINE.json configs[2..3]); not part of the reference constructor, set as an attribute
+        self.conv_precision = "fp32"
         c = channels
         self.encoder = Encoder(in_channel=in_channel, first_out_channel=c)
         self.upsample = nn.Upsample(scale_factor=2, mode="nearest")
@@ -274,10 +277,11 @@ class ModeT(nn.Module):
         return super().train(mode)
 
     def forward(self, moving, fixed):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            return self._forward_train(moving, fixed)
-        with ops.stats_arena(moving.device):
-            return self._forward_infer(moving, fixed)
+        with ops.conv_precision(self.conv_precision):
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                return self._forward_train(moving, fixed)
+            with ops.stats_arena(moving.device):
+                return self._forward_infer(moving, fixed)
 
     def _forward_infer(self, moving, fixed):
         B = moving.shape[0]

@@ -251,6 +251,35 @@ def _prepared_weights(weight: Tensor, Cin: int, Cout: int) -> Optional[Tensor]:
     return wprep
 
 
+# Precision of the MMA operands of conv3d: "fp32" (default: fp32 SIMT kernels + 3xTF32 tcgen05, fp32-class results) or
+# "bf16" (tcgen05 kind::f16 with fp32 accumulation, csrc/conv_bf16.cu: BASELINE.json configs[2..3]).  Activations,
+# statistics and every other operator stay fp32.  Set through the context manager below or `ModeT.conv_precision`.
+_CONV_PRECISION = "fp32"
+
+
+def current_conv_precision() -> str:
+    return _CONV_PRECISION
+
+
+class conv_precision:
+    """with ops.conv_precision("bf16"): ...   -- conv3d (forward and the data-gradient pass) on bf16 tensor cores."""
+
+    def __init__(self, mode: str):
+        if mode not in ("fp32", "bf16"):
+            raise ValueError(f"conv precision must be 'fp32' or 'bf16', got {mode!r}")
+        self.mode = mode
+
+    def __enter__(self):
+        global _CONV_PRECISION
+        self.prev, _CONV_PRECISION = _CONV_PRECISION, self.mode
+        return self
+
+    def __exit__(self, *exc):
+        global _CONV_PRECISION
+        _CONV_PRECISION = self.prev
+        return False
+
+
 def conv3d(x: Tensor, weight: Tensor, bias: Tensor, in_stats: Optional[Tensor] = None, want_stats: bool = False,
            act_out: bool = False, eps: float = IN_EPS) -> Tuple[Tensor, Optional[Tensor]]:
     """Conv3d(k=3, s=1, p=1) (ModeT/models.py:127, 143, 253).  With `in_stats` the input is a raw conv
@@ -270,6 +299,10 @@ def conv3d(x: Tensor, weight: Tensor, bias: Tensor, in_stats: Optional[Tensor] =
             raise SmileError("in_stats must be [B*Cin, 2] float64")
     out = torch.empty((B, Cout, D, H, W), device=x.device, dtype=torch.float32)
     stats = stats_arena.take(B * Cout, x.device) if want_stats else None
+    if _CONV_PRECISION == "bf16":
+        call("smile_conv3d_bf16_fwd", x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), _ptr(in_stats),
+             _ptr(stats), B, Cin, Cout, D, H, W, int(act_out), float(eps), _stream(), label=f"[{Cin}->{Cout} {D}x{H}x{W}]")
+        return out, stats
     wprep = _prepared_weights(weight_in, Cin, Cout) if weight is weight_in else None
     if wprep is not None:
         call("smile_conv3d_prepped_fwd", x.data_ptr(), weight.data_ptr(), wprep.data_ptr(), bias.data_ptr(), out.data_ptr(),

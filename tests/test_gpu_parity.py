@@ -517,3 +517,64 @@ def test_registration_pipeline_matches_direct_calls():
     with torch.no_grad():
         want = [int(metrics.jacobian_determinant_vxm(f.cuda(), want_det=False)[1]) for _, f in direct]
     assert fracs == want
+
+
+# ------------------------------------------------------------------ bf16 tensor-core convolution (configs[2..3])
+@pytest.mark.parametrize("cin,cout,shape", [(8, 8, (6, 10, 40)), (16, 16, (5, 12, 20)), (4, 8, (4, 9, 33)), (32, 32, (4, 6, 10)),
+                                            (64, 64, (3, 5, 6)), (128, 128, (2, 3, 4)), (12, 2, (4, 8, 10)), (24, 24, (3, 7, 9)),
+                                            (48, 8, (3, 4, 5)), (8, 16, (4, 6, 80)), (16, 32, (2, 48, 40))])
+def test_conv3d_bf16_tensor_cores(ops, cin, cout, shape, monkeypatch):
+    """kind::f16 MMA with fp32 accumulation: only the operands of the products are rounded to bf16, so the result must
+    match a reference whose inputs and weights were rounded to bf16 to fp32-accumulation accuracy (<= 2e-5 relative),
+    and the unrounded fp32 convolution to bf16 accuracy (<= 1e-2 relative of the output scale; typically 2-3e-3)."""
+    monkeypatch.setenv("SMILE_CONV_BF16", "2")     # the kernel itself, also on shapes the dispatcher leaves to fp32
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, cin, *shape, generator=g)
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    r = lambda t: t.to(torch.bfloat16).to(torch.float32)
+    with ops.conv_precision("bf16"):
+        out, stats = ops.conv3d(dev(x), dev(w), dev(b), want_stats=True)
+    out = out.cpu()
+    ref_rounded = orc.conv3(r(x).double(), r(w).double(), b.double()).float()
+    ref_fp32 = orc.conv3(x, w, b)
+    assert rel_err(out, ref_rounded) <= 2e-5, (cin, cout, shape)
+    assert rel_err(out, ref_fp32) <= 1e-2
+    s = stats.cpu().reshape(2, cout, 2)
+    assert torch.allclose(s[..., 0], out.double().sum(dim=(2, 3, 4)), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(s[..., 1], (out.double() ** 2).sum(dim=(2, 3, 4)), rtol=1e-5, atol=1e-3)
+    # normalise-on-load + LeakyReLU on store
+    st_in = torch.stack([x.double().sum((2, 3, 4)).flatten(), (x.double() ** 2).sum((2, 3, 4)).flatten()], 1).contiguous()
+    xn = orc.lrelu(orc.instance_norm(x))
+    with ops.conv_precision("bf16"):
+        out2, _ = ops.conv3d(dev(x), dev(w), dev(b), in_stats=dev(st_in), act_out=True)
+    ref2 = orc.lrelu(orc.conv3(r(xn).double(), r(w).double(), b.double()).float())
+    assert rel_err(out2.cpu(), ref2) <= 2e-3      # the normalised activation is rounded to bf16 after a fp32 fma: 1-ulp flips
+
+
+def test_bf16_forward_and_training_step_track_fp32():
+    """ModeT with conv_precision='bf16' (configs[2..3]): forward flow within 0.15 voxels (max-abs; |flow| reaches ~6) of the
+    fp32 path at 32x48x32 -- bf16 products perturb the features by ~1e-3 relative and the five-level cascade amplifies that
+    like any other rounding (measured 6e-2 here, 0.12 at 160x192x160) -- and three training steps whose losses follow the
+    fp32 run to 2e-3 (loss-curve agreement on synthetic data)."""
+    from smilecode_b200 import models
+    from smilecode_b200.synth import make_pair, randomize_weights
+    from smilecode_b200.train import Trainer
+    shape, heads = (32, 48, 32), [8, 4, 2, 1, 1]
+    moving, fixed = (dev(t) for t in make_pair(shape, batch=2, seed=24))
+    flows, losses = {}, {}
+    for prec in ("fp32", "bf16"):
+        torch.manual_seed(0)
+        m = models.ModeT(shape, head_dim=6, num_heads=heads, scale=1)
+        randomize_weights(m, seed=1234)
+        m = m.cuda()
+        m.conv_precision = prec
+        with torch.no_grad():
+            m.eval()
+            flows[prec] = m(moving, fixed)[1].cpu()
+        tr = Trainer(m, lr=1e-4)
+        losses[prec] = [float(tr.step(moving, fixed)[0]) for _ in range(3)]
+    d = float((flows["bf16"] - flows["fp32"]).abs().max())
+    print(f"\nbf16 vs fp32: max|flow diff| {d:.3e} voxels (|flow| max {float(flows['fp32'].abs().max()):.2f}); losses {losses}")
+    assert d <= 0.15
+    assert all(abs(a - b) <= 2e-3 * max(1.0, abs(a)) for a, b in zip(losses["fp32"], losses["bf16"]))

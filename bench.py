@@ -454,40 +454,54 @@ def main():
                     print(f"  {ms:9.3f} ms  {100 * ms / tot:5.1f}%  x{calls:<3d} {name}", file=sys.stderr)
                 print(f"  total of kernels {tot:.3f} ms", file=sys.stderr)
 
-    # ---------------- training step: fp32, one pair per GPU, NCC + Grad3d loss, hand-written
-    # backward kernels, one flat-bucket NCCL all-reduce of the gradients when N > 1, fused Adam(amsgrad) update
-    train = None
+    # ---------------- training step: NCC + Grad3d loss, hand-written backward kernels, one
+    # flat-bucket NCCL all-reduce of the gradients when N > 1, fused Adam(amsgrad) update.  Two blocks:
+    #   train       fp32, --train-batch pairs per GPU (default 1: the reference's own recipe, train.py:43)
+    #   train_bf16  BASELINE.json configs[2] at N = 1 (batch 8 on one GPU) / configs[3] at N > 1 (global batch 32, sharded by
+    #               batch): Conv3d forward + data-gradient products on bf16 tensor cores (tcgen05 kind::f16), fp32 accumulate
+    train, train_bf16 = None, None
     if not args.no_train:
         from smilecode_b200.train import Trainer
-        tmodel = models.ModeT(SHAPE, head_dim=6, num_heads=HEADS, scale=1)
-        randomize_weights(tmodel, seed=1234)
-        tmodel = tmodel.to(dev)
-        tmodel.conv_precision = args.train_dtype
-        trainer = Trainer(tmodel, lr=1e-4, distributed=world > 1)
-        TB = max(1, args.train_batch)
-        if TB > 1:
-            mvs, fxs = zip(*[make_pair(SHAPE, batch=1, seed=24 + rank + 100 * i) for i in range(TB)])
-            moving, fixed = torch.cat(mvs).to(dev), torch.cat(fxs).to(dev)
-        for _ in range(2):
-            trainer.step(moving, fixed)
-        barrier()
-        l0 = _lib.LAUNCHES
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        TK = min(K, 5)
-        t0.record(stream)
-        for _ in range(TK):
-            tloss, _, _ = trainer.step(moving, fixed)
-        t1.record(stream)
-        barrier()
-        tms = reduce_max(t0.elapsed_time(t1)) / TK
-        train = {"value": world * TB * 1e3 / tms, "unit": "pairs/s", "ms_per_step": tms, "steps": TK,
-                 "pairs_per_gpu_per_step": TB, "global_pairs_per_step": TB * world,
-                 "dtype": "f32" if args.train_dtype == "fp32" else "bf16 conv MMA operands (tcgen05 kind::f16), f32 accumulation / activations / everything else",
-                 "gpu_launches_per_step": (_lib.LAUNCHES - l0) // TK, "loss": float(tloss),
-                 "config": f"{args.train_dtype} training step, {TB} pair(s) per GPU, NCC_vxm(9) + Grad3d(l2), Adam(amsgrad); "
-                           + ("flat-bucket NCCL gradient all-reduce" if world > 1 else "single GPU, no collective")}
-        del trainer, tmodel
-        torch.cuda.empty_cache()
+
+        def train_leg(dtype: str, TB: int, label: str):
+            tmodel = models.ModeT(SHAPE, head_dim=6, num_heads=HEADS, scale=1)
+            randomize_weights(tmodel, seed=1234)
+            tmodel = tmodel.to(dev)
+            tmodel.conv_precision = dtype
+            trainer = Trainer(tmodel, lr=1e-4, distributed=world > 1)
+            mv, fx = moving, fixed
+            if TB > 1:
+                mvs, fxs = zip(*[make_pair(SHAPE, batch=1, seed=24 + rank + 100 * i) for i in range(TB)])
+                mv, fx = torch.cat(mvs).to(dev), torch.cat(fxs).to(dev)
+            for _ in range(2):
+                trainer.step(mv, fx)
+            barrier()
+            l0 = _lib.LAUNCHES
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            TK = min(K, 5)
+            t0.record(stream)
+            for _ in range(TK):
+                tloss, _, _ = trainer.step(mv, fx)
+            t1.record(stream)
+            barrier()
+            tms = reduce_max(t0.elapsed_time(t1)) / TK
+            out = {"value": world * TB * 1e3 / tms, "unit": "pairs/s", "ms_per_step": tms, "steps": TK,
+                   "pairs_per_gpu_per_step": TB, "global_pairs_per_step": TB * world,
+                   "dtype": "f32" if dtype == "fp32" else "bf16 conv MMA operands (tcgen05 kind::f16), f32 accumulation / "
+                                                         "activations / everything else",
+                   "gpu_launches_per_step": (_lib.LAUNCHES - l0) // TK, "loss": float(tloss),
+                   "config": f"{label}: {dtype} training step, {TB} pair(s) per GPU, NCC_vxm(9) + Grad3d(l2), Adam(amsgrad); "
+                             + ("flat-bucket NCCL gradient all-reduce" if world > 1 else "single GPU, no collective")}
+            del trainer, tmodel, mv, fx
+            torch.cuda.empty_cache()
+            return out
+
+        train = train_leg(args.train_dtype, max(1, args.train_batch), "reference recipe (train.py:43, batch 1)"
+                          if args.train_batch <= 1 else "batched")
+        if args.config == "lpba":
+            tb = 8 if world == 1 else max(1, 32 // world)
+            train_bf16 = train_leg("bf16", tb, "BASELINE.json configs[2] (batch-8 bf16 step, 1 GPU)" if world == 1 else
+                                   f"BASELINE.json configs[3] (global batch {tb * world} bf16 sharded over {world} GPUs)")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -526,7 +540,8 @@ def main():
                         "ms_per_step": e2e_ms_step,
                         "what": "RegistrationPipeline(outputs=('flow',)): pair up from pinned host memory, flow down into "
                                 "pinned host memory (what infer.py:79-89 moves per pair)", "other_modes": e2e_modes},
-                "step_ms_min_max": [min(step_ms), max(step_ms)], "gpu_launches": launches, "gpu_launches_per_step": launches // K, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "train": train, "batched": batched, "bf16_forward": bf16_fwd,
+                "step_ms_min_max": [min(step_ms), max(step_ms)], "gpu_launches": launches, "gpu_launches_per_step": launches // K, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "train": train, "train_bf16": train_bf16, "batched": batched,
+                "bf16_forward": bf16_fwd,
                 "comparators": comparators}
         if breakdown:
             line["kernel_ms"] = {name: round(ms, 4) for ms, _, name in breakdown[:12]}

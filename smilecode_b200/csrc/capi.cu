@@ -4,6 +4,8 @@
 
 #include "../../include/smilecode_b200.h"
 #include "common.cuh"
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace smile {
@@ -172,6 +174,13 @@ int smile_conv3d_bf16_fwd(const float* in, const float* weight, const float* bia
   REQUIRE(in != out, "%s: out must not alias in", __func__);
   REQUIRE((long long)B <= 65535, "%s: B=%d exceeds grid.z", __func__, B);
   bool handled = false;
+  // few channels (the wide levels): depth-marching kernel; otherwise the plane-tiled kernel where it wins
+  const char* march = getenv("SMILE_CONV_MARCH");
+  if (march == nullptr || march[0] != '0') {
+    const int rc = launch_conv3d_march_bf16(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps,
+                                            (cudaStream_t)stream, &handled);
+    if (handled) return rc;
+  }
   const int rc = launch_conv3d_bf16(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps,
                                     (cudaStream_t)stream, &handled);
   if (handled) return rc;

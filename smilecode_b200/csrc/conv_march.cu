@@ -1,0 +1,417 @@
+// Conv3d 3x3x3 / pad 1 for the WIDE, few-channel levels (Cin <= 16, Cout <= 16: the 160- and 80-wide encoder / CWM layers,
+// 70 % of the convolution time) with bf16 operands on tcgen05 -- the depth-marching counterpart of conv_bf16.cu.
+//
+// conv_bf16.cu stages three padded planes per 128 outputs; on a 160-wide volume that is 10 staged positions per output
+// and the kernel is 5-10x slower than the fp32 SIMT path (profiles/r03e_conv_compare.txt).  Here a CTA owns a 16-row x
+// 30-column tile of the (H, W) plane and marches it along D:
+//   * every input plane of the tile (18 x 32 positions with halo, position-major, 16 bf16 channels = 2 x 16 bytes per
+//     position) is staged ONCE into a ring of four planes -- 1.2 staged positions per output;
+//   * with Cin <= 16 the whole reduction over input channels is one K = 16 MMA per tap: 27 MMAs per 128-position M tile,
+//     four M tiles (4 rows x 32 padded columns each) per plane; a tap (kd, kh, kw) is ring slot kd and the shifted
+//     start address (kh * 32 + kw) * 16 B of a K-major no-swizzle A descriptor, as in conv_tc.cu / conv_bf16.cu;
+//   * two TMEM accumulator buffers (4 x 16 columns each) and a dedicated MMA-issuing warp: the MMAs of plane d run while
+//     the eight worker warps stage plane d+2 and drain, bias-add and store plane d-1; the hand-overs are mbarriers
+//     (plane staged -> issuer, MMAs done -> workers, buffer drained -> issuer), there is no CTA-wide barrier in the loop;
+//   * InstanceNorm statistics of the raw output are kept in registers for the whole march and reduced once.
+// Contract identical to smile_conv3d_bf16_fwd (NCDHW fp32 in / out, normalise-on-load, fp64 statistics).
+#include <cuda_bf16.h>
+
+#include <cstdint>
+#include <cstdlib>
+#include <mutex>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace smile {
+namespace {
+
+constexpr int P = 32;                 // padded pitch of a staged row (30 output columns + 2)
+constexpr int TC = P - 2;             // output columns per tile
+constexpr int MT = 4;                 // M tiles (128 positions = 4 rows) per plane
+constexpr int TR = 4 * MT;            // output rows per tile
+constexpr int SROWS = TR + 2;         // staged rows
+constexpr int PLANE_POS = 592;        // staged positions per plane (18 * 32 = 576, + the overhang of the last taps)
+constexpr int PLANE_BYTES = 2 * PLANE_POS * 16;   // two channel blocks of 8 bf16
+constexpr int RING = 4;
+constexpr int NT = 16;                // output channels (UMMA N)
+constexpr int B_BYTES = 27 * 2 * NT * 16;
+constexpr int WORKERS = 256;          // warps 0-7 stage the planes and drain the accumulators
+constexpr int THREADS = WORKERS + 32; // warp 8 only issues the MMAs (one lane): 108 per plane would otherwise delay warp 0
+constexpr int OFF_B = RING * PLANE_BYTES;
+// [0] weights landed, [1..2] MMAs of TMEM buffer 0 / 1 done, [3..4] plane staged (by step parity), [5..6] TMEM buffer drained
+constexpr int OFF_BAR = OFF_B + B_BYTES;
+constexpr int OFF_TMEM = OFF_BAR + 64;
+constexpr int OFF_MR = OFF_TMEM + 16;              // [16][2] rstd, -mean * rstd
+constexpr int OFF_RED = OFF_MR + 128 + 64;         // (+ 16 bias values); [8 warps][16][2] doubles
+constexpr int SMEM = OFF_RED + 8 * 16 * 2 * 8 + 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// weight [Cout][Cin][27] fp32 -> bf16 B operands.
+//   Cin > 8 : [tap 27][cb 2][NT][8], input channel ci = cb*8 + j (one K = 16 MMA per tap).
+//   Cin <= 8: [mma 15][cb 2][NT][8]: two TAPS share a K = 16 MMA -- channel block 0 holds tap t, block 1 tap t+1 of the same
+//             plane (A's second K chunk is the same staged plane shifted by the tap distance, see the issuer), the ninth
+//             tap of a plane goes alone with a zero second block: 15 MMAs per M tile instead of 27.
+__device__ __forceinline__ int pair_first_tap(int i) { return (i / 5) * 9 + (i % 5) * 2; }   // mma i of 15 -> its first tap
+__global__ void conv_march_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wprep, int Cout, int Cin) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 27 * 2 * NT * 8) return;
+  int t = e;
+  const int j = t % 8; t /= 8;
+  const int n = t % NT; t /= NT;
+  const int cb = t % 2; t /= 2;
+  float v = 0.f;
+  if (Cin > 8) {
+    const int tap = t, ci = cb * 8 + j;
+    if (ci < Cin && n < Cout) v = w[((long long)n * Cin + ci) * 27 + tap];
+  } else if (t < 15) {
+    const int t0 = pair_first_tap(t);
+    const bool single = (t % 5) == 4;
+    const int tap = t0 + cb;
+    if (!(single && cb == 1) && j < Cin && n < Cout) v = w[((long long)n * Cin + j) * 27 + tap];
+  }
+  wprep[e] = __float2bfloat16_rn(v);
+}
+
+// CIN8: at most 8 input channels (the second channel block stays zero); NORM: InstanceNorm + LeakyReLU on load
+template <bool CIN8, bool NORM>
+__global__ void __launch_bounds__(THREADS, 2)
+conv_march_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict__ wprep, const float* __restrict__ bias,
+                  float* __restrict__ out, const double* __restrict__ in_stats, double* __restrict__ out_stats, int Cin,
+                  int Cout, int D, int H, int W, int ntr, int ntc, int DS, int act_out, float eps) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+  float* s_mr = reinterpret_cast<float*>(smem + OFF_MR);
+  double* s_red = reinterpret_cast<double*>(smem + OFF_RED);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HW = H * W;
+  const long long N = (long long)D * HW;
+  int t = blockIdx.x;
+  const int ds = t % DS; t /= DS;
+  const int tc = t % ntc; t /= ntc;
+  const int tr = t % ntr; t /= ntr;
+  const int b = t;
+  const int h0 = tr * TR, w0 = tc * TC;
+  const int dlen = ceil_div(D, DS);
+  const int d0 = ds * dlen, d1 = min(D, d0 + dlen);
+  if (d0 >= d1) return;   // uniform per CTA
+
+  if (tid == 0) {
+    for (int i = 0; i < 3; ++i) mbar_init(smem_u32(bars + i), 1);
+    for (int i = 3; i < 7; ++i) mbar_init(smem_u32(bars + i), WORKERS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(smem_u32(bars), B_BYTES);
+    bulk_g2s(smem_u32(smem + OFF_B), wprep, B_BYTES, smem_u32(bars));
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid < 16) {
+    float rstd = 1.f, shift = 0.f;
+    if (NORM && tid < Cin) {
+      const double s = in_stats[((long long)b * Cin + tid) * 2], ss = in_stats[((long long)b * Cin + tid) * 2 + 1];
+      const double mean = s / (double)N;
+      const double var = fmax(ss / (double)N - mean * mean, 0.0);
+      rstd = (float)(1.0 / sqrt(var + (double)eps));
+      shift = -(float)mean * rstd;
+    }
+    s_mr[2 * tid] = rstd;
+    s_mr[2 * tid + 1] = shift;
+  }
+  // zero the ring once: the unused channel block, the overhang and the out-of-volume positions stay zero
+  for (int i = tid; i < RING * PLANE_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  const float* inb = in + (long long)b * Cin * N;
+  constexpr int NCH = CIN8 ? 8 : 16;
+  constexpr int PB = (CIN8 ? 1 : 2) * PLANE_POS * 16;     // bytes of one staged plane (one or two channel blocks)
+
+  // ---- stage one input plane (global depth dd) into its ring slot
+  auto stage_plane = [&](int dd) {
+    uint4* slot = reinterpret_cast<uint4*>(smem + (size_t)((dd + RING) % RING) * PB);
+    const bool plane_ok = dd >= 0 && dd < D;
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+      const int i = tid + it * WORKERS;
+      if (i >= SROWS * P) break;
+      const int r = i >> 5, c = i & 31;
+      const int h = h0 - 1 + r, w = w0 - 1 + c;
+      float v[NCH];
+      const bool ok = plane_ok && h >= 0 && h < H && w >= 0 && w < W;
+      if (ok) {
+        const float* p = inb + (long long)dd * HW + h * W + w;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) v[j] = (j < Cin) ? __ldg(p + (long long)j * N) : 0.f;
+        if (NORM) {
+#pragma unroll
+          for (int j = 0; j < NCH; ++j) {
+            const float x = fmaf(v[j], s_mr[2 * j], s_mr[2 * j + 1]);   // broadcast shared-memory reads
+            v[j] = (j < Cin) ? fmaxf(x, 0.1f * x) : 0.f;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) v[j] = 0.f;
+      }
+      slot[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      if (!CIN8)
+        slot[PLANE_POS + i] =
+            make_uint4(pack_bf16(v[8 % NCH], v[9 % NCH]), pack_bf16(v[10 % NCH], v[11 % NCH]), pack_bf16(v[12 % NCH], v[13 % NCH]),
+                       pack_bf16(v[14 % NCH], v[15 % NCH]));
+    }
+  };
+
+  // epilogue ownership: TMEM lane quadrant q = warp % 4 (row 4m + q of M tile m), M tiles 2*(warp / 4) and + 1
+  const int q = warp & 3, mbase = 2 * (warp >> 2);
+  const bool col_ok = lane < TC && (w0 + lane) < W;
+  float* s_bias = s_mr + 32;
+  if (tid < NT) s_bias[tid] = (tid < Cout) ? __ldg(bias + tid) : 0.f;
+  __syncthreads();
+  float st_s[NT], st_q[NT];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) st_s[n] = st_q[n] = 0.f;
+
+  auto drain_plane = [&](int dd, int buf) {
+#pragma unroll
+    for (int mm = 0; mm < 2; ++mm) {
+      const int m = mbase + mm;
+      const int h = h0 + 4 * m + q;
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * (MT * NT) + m * NT);
+      uint32_t r[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (col_ok && h < H) {
+        float* ob = out + (long long)b * Cout * N + (long long)dd * HW + h * W + (w0 + lane);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          if (n < Cout) {
+            const float val = __uint_as_float(r[n]) + s_bias[n];
+            ob[(long long)n * N] = act_out ? lrelu01(val) : val;
+            st_s[n] += val;
+            st_q[n] = fmaf(val, val, st_q[n]);
+          }
+        }
+      }
+    }
+  };
+
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t ring_base = smem_u32(smem), b_base = smem_u32(smem + OFF_B);
+
+  auto arrive = [&](int bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bars + bar)) : "memory"); };
+
+  if (warp < 8) {
+    // ---------------- workers: stage plane d+1, then drain plane d-1 while the MMAs of plane d run
+    stage_plane(d0 - 1);
+    stage_plane(d0);
+    uint32_t ph[2] = {0u, 0u};
+    for (int d = d0; d < d1; ++d) {
+      const int par = (d - d0) & 1;
+      stage_plane(d + 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      arrive(3 + par);                                               // planes d-1, d, d+1 are in the ring
+      if (d > d0) {
+        const int pb = par ^ 1;
+        mbar_wait(smem_u32(bars + 1 + pb), ph[pb]);                  // MMAs of plane d-1 complete
+        ph[pb] ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        drain_plane(d - 1, pb);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        arrive(5 + pb);                                              // TMEM buffer pb may be overwritten
+      }
+    }
+    {
+      const int pb = (d1 - 1 - d0) & 1;
+      mbar_wait(smem_u32(bars + 1 + pb), ph[pb]);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      drain_plane(d1 - 1, pb);
+    }
+  } else if (lane == 0) {
+    // ---------------- issuer: 4 x 27 MMAs per plane
+    mbar_wait(smem_u32(bars), 0);   // weights
+    uint32_t ph_s[2] = {0u, 0u}, ph_d[2] = {0u, 0u};
+    for (int d = d0; d < d1; ++d) {
+      const int par = (d - d0) & 1;
+      mbar_wait(smem_u32(bars + 3 + par), ph_s[par]);
+      ph_s[par] ^= 1u;
+      if (d - d0 >= 2) {            // the accumulator buffer was last used by plane d-2: drained?
+        mbar_wait(smem_u32(bars + 5 + par), ph_d[par]);
+        ph_d[par] ^= 1u;
+      }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // Descriptors differ only in their 14-bit start-address field (16-byte units) -- and, for the paired taps of the
+      // Cin <= 8 variant, in the leading-dimension offset = distance between the two taps in the staged plane.
+      uint32_t slot16[3];
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd) slot16[kd] = (ring_base + (uint32_t)(((d - 1 + kd + RING) % RING) * PB)) >> 4;
+      const uint64_t db0 = make_desc(b_base, NT * 16, 128);
+#define SMILE_MMA(DCOL, DA, DB, FIRST)                                                                                     \
+  if (FIRST)                                                                                                               \
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" \
+                 ::"r"(DCOL), "l"(DA), "l"(DB), "r"(idesc) : "memory");                                                    \
+  else                                                                                                                     \
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" \
+                 ::"r"(DCOL), "l"(DA), "l"(DB), "r"(idesc) : "memory");
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        const uint32_t dcol = tmem + (uint32_t)(par * (MT * NT) + m * NT);
+        if (CIN8) {
+          const uint64_t da_row = make_desc(0u, 16, 128), da_wrap = make_desc(0u, (P - 2) * 16, 128);
+#pragma unroll
+          for (int i = 0; i < 15; ++i) {
+            const int kd = i / 5, t0 = (i % 5) * 2;            // first tap of the pair inside the plane: 0 2 4 6 8
+            const int kh = t0 / 3, kw = t0 % 3;
+            // second tap t0 + 1: next column (distance 1 position) unless t0 ends a row (distance P - 2)
+            const uint64_t hi = (kw == 2 && t0 != 8) ? da_wrap : da_row;   // the lone ninth tap: zero weights on chunk 2
+            const uint64_t da = hi + (uint64_t)(slot16[kd] + (uint32_t)(m * 128 + kh * P + kw));
+            const uint64_t db = db0 + (uint64_t)(i * 2 * NT);
+            SMILE_MMA(dcol, da, db, i == 0)
+          }
+        } else {
+          const uint64_t da_hi = make_desc(0u, PLANE_POS * 16, 128);
+#pragma unroll
+          for (int tap = 0; tap < 27; ++tap) {
+            const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+            const uint64_t da = da_hi + (uint64_t)(slot16[kd] + (uint32_t)(m * 128 + kh * P + kw));
+            const uint64_t db = db0 + (uint64_t)(tap * 2 * NT);
+            SMILE_MMA(dcol, da, db, tap == 0)
+          }
+        }
+      }
+#undef SMILE_MMA
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bars + 1 + par))
+                   : "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(128));
+
+  // ---- InstanceNorm statistics: warp shuffle -> shared -> one fp64 atomic per channel and CTA
+  if (out_stats != nullptr) {
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      if (warp >= 8) break;
+      float s = st_s[n], sq = st_q[n];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      }
+      if (lane == 0) {
+        s_red[(warp * NT + n) * 2] = (double)s;
+        s_red[(warp * NT + n) * 2 + 1] = (double)sq;
+      }
+    }
+    __syncthreads();
+    if (tid < 2 * NT) {
+      const int n = tid >> 1, which = tid & 1;
+      if (n < Cout) {
+        double tot = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) tot += s_red[(wv * NT + n) * 2 + which];
+        atomicAdd(out_stats + ((long long)b * Cout + n) * 2 + which, tot);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// Depth-marching bf16 tensor-core conv for Cin <= 16 and Cout <= 16.  *handled = false otherwise.
+int launch_conv3d_march_bf16(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
+                             double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
+                             cudaStream_t st, bool* handled) {
+  *handled = false;
+  if (Cin < 2 || Cin > 16 || Cout > 16 || D < 1 || H < 2 || W < 2) return SMILE_OK;
+  *handled = true;
+  const int ntr = ceil_div(H, TR), ntc = ceil_div(W, TC);
+  const long long tiles = (long long)B * ntr * ntc;
+  // Two CTAs per SM (92 KB of shared memory, 128 TMEM columns each): while one stages / drains, the other's MMAs run.
+  // The depth is split so that the grid is just under two full waves of 2 x 148 CTAs (measured: 288-576 CTAs beat 144
+  // and anything that leaves a partial third wave; each split re-stages two halo planes, which is not what bounds it).
+  static const int want = [] { const char* e = getenv("SMILE_MARCH_CTAS"); return e ? atoi(e) : 4 * kNumSMs; }();
+  int DS = (int)(want / tiles);
+  if (DS > D / 4) DS = D / 4;
+  if (DS < 1) DS = 1;
+  static std::once_flag once[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::call_once(once[dev & 63], [dev] {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t cur = 0, want = 64ull << 20;
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur);
+      if (cur < want) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &want);
+    }
+  });
+  __nv_bfloat16* wprep = nullptr;
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&wprep), B_BYTES, st);
+  if (e != cudaSuccess) {
+    set_error("conv3d(bf16 march): cudaMallocAsync failed: %s", cudaGetErrorString(e));
+    return SMILE_ERR_CUDA;
+  }
+  conv_march_prep_kernel<<<ceil_div(27 * 2 * NT * 8, 256), 256, 0, st>>>(weight, wprep, Cout, Cin);
+  const unsigned grid = (unsigned)(tiles * DS);
+  auto run = [&](auto kern) {
+    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e2 != cudaSuccess) {
+      set_error("conv3d(bf16 march): cannot reserve %d B of shared memory: %s", SMEM, cudaGetErrorString(e2));
+      return SMILE_ERR_CUDA;
+    }
+    kern<<<grid, THREADS, SMEM, st>>>(in, wprep, bias, out, in_stats, out_stats, Cin, Cout, D, H, W, ntr, ntc, DS, act_out, eps);
+    return check_launch("conv3d(bf16 march)");
+  };
+  int rc;
+  if (Cin <= 8)
+    rc = in_stats ? run(conv_march_kernel<true, true>) : run(conv_march_kernel<true, false>);
+  else
+    rc = in_stats ? run(conv_march_kernel<false, true>) : run(conv_march_kernel<false, false>);
+  cudaFreeAsync(wprep, st);
+  return rc;
+}
+
+}  // namespace smile

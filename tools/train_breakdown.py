@@ -14,6 +14,8 @@ SHAPE = (160, 192, 160)
 model = models.ModeT(SHAPE, head_dim=6, num_heads=[8, 4, 2, 1, 1], scale=1)
 randomize_weights(model, seed=1234)
 model = model.to(dev)
+import os
+model.conv_precision = os.environ.get("SMILE_TRAIN_DTYPE", "fp32")
 tr = Trainer(model, lr=1e-4)
 moving, fixed = [t.to(dev) for t in make_pair(SHAPE, batch=1, seed=24)]
 for _ in range(2):

@@ -73,10 +73,12 @@ class ModeTransformer(nn.Module):
         self.register_buffer("grid", torch.stack(torch.meshgrid(off, off, off, indexing="ij"), -1))
 
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
-        # ModeT-cu checkpoints carry the tap offsets as `v` [27,3] instead of `grid` [3,3,3,3]
-        v = state_dict.pop(prefix + "v", None)
-        if v is not None and prefix + "grid" not in state_dict:
-            state_dict[prefix + "grid"] = v.reshape(3, 3, 3, 3)
+        # ModeT checkpoints carry the tap offsets as `grid` [3,3,3,3], ModeT-cu ones as `v` [27,3]: accept either, whichever
+        # buffer this instance registers (ModeT: grid, ModeT_cu: v)
+        mine, other = ("v", "grid") if "v" in self._buffers else ("grid", "v")
+        t = state_dict.pop(prefix + other, None)
+        if t is not None and prefix + mine not in state_dict:
+            state_dict[prefix + mine] = t.reshape(27, 3) if mine == "v" else t.reshape(3, 3, 3, 3)
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
     def forward(self, q, k):
@@ -315,10 +317,18 @@ class ModeT(nn.Module):
 
 
 class ModeT_cu(ModeT):
-    """Name used by the reference's ModeT-cu/train.py:14 (default scale=1, ModeT-cu/models.py:325)."""
+    """Name used by the reference's ModeT-cu/train.py:14 (default scale=1, ModeT-cu/models.py:325).  Its state_dict carries
+    the tap offsets as `mdtN.v` [27,3] like ModeT-cu/models.py:296-299 (not `mdtN.grid` [3,3,3,3] as ModeT does), so a
+    checkpoint written here loads with strict=True into the reference's ModeT_cu and vice versa; `grid` is accepted on
+    load too (ModeTransformer._load_from_state_dict handles both spellings)."""
 
     def __init__(self, inshape=(160, 192, 160), in_channel=1, channels=4, head_dim=6, num_heads=[8, 4, 2, 1, 1], scale=1):
         super().__init__(inshape, in_channel, channels, head_dim, num_heads, scale)
+        for level in range(1, 6):
+            mdt = getattr(self, f"mdt{level}")
+            g = mdt.grid
+            del mdt._buffers["grid"]
+            mdt.register_buffer("v", g.reshape(27, 3).clone())
 
 
 # ------------------------------------------------------------------------------------------------

@@ -103,6 +103,13 @@ def test_state_dict_contract():
     m2 = models.ModeT_cu((32, 32, 32))
     assert m2.mdt1.scale == 1
     m2.load_state_dict(cu, strict=True)
+    # ... and ModeT_cu writes it that way too (the -cu contract used to hold in one direction only); either
+    # class loads either spelling
+    sd_cu = m2.state_dict()
+    assert sorted(k for k in sd_cu if k.startswith("mdt") and not k.endswith("rpb")) == [f"mdt{i}.v" for i in range(1, 6)]
+    assert tuple(sd_cu["mdt2.v"].shape) == (27, 3)
+    m2.load_state_dict(sd, strict=True)          # ModeT checkpoint (grid) into ModeT_cu
+    m.load_state_dict(sd_cu, strict=True)        # ModeT_cu checkpoint (v) into ModeT
     for name in ("Encoder", "ProjectionLayer", "ConvBlock", "ConvInsBlock", "VecInt", "ResizeTransform", "UpConvBlock",
                  "DeconvBlock", "CWM", "ModeTransformer", "SpatialTransformer"):
         assert hasattr(models, name)

@@ -55,3 +55,20 @@ def test_reference_train_py_runs_on_dropin(tmp_path):
     assert out["optimizer_steps"] == 5 and out["our_kernel_launches"] > 1000
     assert len(out["checkpoints"]) >= 1                          # save_checkpoint at the end of an epoch (train.py:155-160)
     assert any("loss" in l for l in out["log_tail"])
+
+
+@needs_ref
+def test_modet_cu_checkpoints_load_strict_both_ways():
+    """ModeT-cu names the tap table `mdtN.v` (ModeT-cu/models.py:296-299): a checkpoint written by either ModeT_cu loads into
+    the other with strict=True."""
+    from oracle import reference_loader as rl
+    from smilecode_b200 import models
+    ref_cu = rl.reference_models_cu()
+    if ref_cu is None:
+        pytest.skip("reference modet extension not built")
+    shape = (32, 32, 32)
+    theirs, ours = ref_cu.ModeT_cu(shape), models.ModeT_cu(shape)
+    assert sorted(theirs.state_dict().keys()) == sorted(ours.state_dict().keys())
+    r1 = ours.load_state_dict(theirs.state_dict(), strict=True)
+    r2 = theirs.load_state_dict(ours.state_dict(), strict=True)
+    assert not r1.missing_keys and not r1.unexpected_keys and not r2.missing_keys and not r2.unexpected_keys

@@ -237,7 +237,10 @@ def _prepared_weights(weight: Tensor, Cin: int, Cout: int) -> Optional[Tensor]:
     cur = torch.cuda.current_stream(weight.device)
     hit = _WPREP_CACHE.get(key) if PREPARED_WEIGHT_CACHE else None
     if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
-        if hit[5] != cur.cuda_stream:          # prepared on another stream: order this stream after the preparation
+        # prepared on another stream and possibly still in flight: order this stream after the preparation (a completed
+        # event needs no edge -- and must not get one while this stream is being captured into a CUDA graph)
+        # (graph.GraphedForward synchronises the device before it starts capturing, so every preparation is complete then)
+        if hit[5] != cur.cuda_stream and not torch.cuda.is_current_stream_capturing() and not hit[4].query():
             cur.wait_event(hit[4])
         return hit[3]
     n = int(lib().smile_conv3d_tc_prep_floats(Cin, Cout))

@@ -22,7 +22,7 @@ import torch
 
 class RegistrationPipeline:
     def __init__(self, model: torch.nn.Module, shape: Sequence[int], depth: int = 3, device=None,
-                 outputs: Sequence[str] = ("flow",), reduce: Optional[Callable] = None):
+                 outputs: Sequence[str] = ("flow",), reduce: Optional[Callable] = None, cuda_graph: bool = True):
         self.model = model
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         if self.device.type != "cuda":
@@ -33,6 +33,10 @@ class RegistrationPipeline:
         self.depth = max(1, int(depth))
         self.outputs = tuple(outputs)
         self.reduce = reduce
+        # one CUDA graph of the forward per device slot (graph.GraphedForward), captured at the slot's first use; the
+        # model's weights must stay as they are while the pipeline lives (cuda_graph=False launches kernel by kernel)
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs: List = [None] * self.depth
         D, H, W = (int(s) for s in shape)
         dev = self.device
         self.s_in = torch.cuda.Stream(dev)
@@ -75,7 +79,16 @@ class RegistrationPipeline:
                 self.fixed_d[s].copy_(fixed, non_blocking=True)
                 self.in_ready[s].record(self.s_in)
             compute.wait_event(self.in_ready[s])
-            moved, flow = self.model(self.moving_d[s], self.fixed_d[s])
+            if self.cuda_graph:
+                if self._graphs[s] is None:
+                    from .graph import GraphedForward
+                    self._graphs[s] = GraphedForward(self.model, self.moving_d[s], self.fixed_d[s])
+                    compute.wait_event(self.in_ready[s])
+                if i >= self.depth:     # the graph's output tensors are reused: their last download must be complete
+                    compute.wait_event(self.out_done[(i - self.depth) % self.nhost])
+                moved, flow = self._graphs[s].replay()
+            else:
+                moved, flow = self.model(self.moving_d[s], self.fixed_d[s])
             red = self.reduce(moved, flow, extra) if self.reduce is not None else None
             self.comp_done[s].record(compute)
             with torch.cuda.stream(self.s_out):
@@ -83,7 +96,8 @@ class RegistrationPipeline:
                 for name, src in (("moved", moved), ("flow", flow)):
                     if name in self.out_h[hs]:
                         self.out_h[hs][name].copy_(src, non_blocking=True)
-                        src.record_stream(self.s_out)
+                        if not self.cuda_graph:
+                            src.record_stream(self.s_out)
                 if isinstance(red, torch.Tensor):      # device result of `reduce`: same asynchronous route to the host
                     if self.red_h[hs] is None or self.red_h[hs].shape != red.shape or self.red_h[hs].dtype != red.dtype:
                         self.red_h[hs] = torch.empty(red.shape, dtype=red.dtype).pin_memory()

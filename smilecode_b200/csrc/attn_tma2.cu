@@ -76,10 +76,16 @@ struct Dims2 {
   int B, D, H, W;
   int ncol_h, ncol_w;
   long long total_units;   // (row band, plane) units: B * ncol_h * D
-  int units_per_cta;       // ... per CTA group
   int group;               // CTAs per group = ncol_w: the W-neighbour columns of a row band march in lockstep
   float dm1, hm1, wm1;
   float rd, rh, rw;
+};
+
+// Work partition, computed on the host: CTA group g marches the (row band, plane) units [u[g], u[g + 1]).  The ranges are
+// balanced by STEPS, not units: a range that crosses the end of a band is two segments and every segment costs two ramp
+// steps (its halo planes), so equal unit counts left the crossing groups 4 steps (9 %) behind the others.
+struct UnitTable {
+  int u[kNumSMs + 1];
 };
 
 // per-pair running softmax state, packed (lo: voxel A, hi: voxel B).  FAST: s, ah, aw are plain sums of exponentials, nd
@@ -161,10 +167,11 @@ __device__ __forceinline__ Corners8b moved_corners_border2(const float* __restri
 }
 
 template <int TH, int NS, bool COMPOSE>
-__device__ __noinline__ int issue_stage2(uint32_t sbase, const Seg* __restrict__ segs, int pseg, int n,
-                                         const CUtensorMap* tm_k, const CUtensorMap* tm_q, const CUtensorMap* tm_f) {
+__device__ __noinline__ void issue_stage2(uint32_t sbase, const Seg* __restrict__ segs, int n, const CUtensorMap* tm_k,
+                                          const CUtensorMap* tm_q, const CUtensorMap* tm_f) {
   using C = Cfg2<TH, NS>;
   constexpr int NF = C::NF;
+  int pseg = 0;
   while (n >= segs[pseg + 1].s_begin) ++pseg;
   const Seg sg = segs[pseg];
   const int p = sg.d_a - 1 + (n - sg.s_begin);
@@ -175,23 +182,20 @@ __device__ __noinline__ int issue_stage2(uint32_t sbase, const Seg* __restrict__
   tma_load_4d(sbase + C::OFF_K + slot * C::K_STRIDE, tm_k, full, (sg.w0 - 2) * HD, sg.h0 - 1, p, sg.b);
   tma_load_4d(sbase + C::OFF_Q + slot * C::Q_STRIDE, tm_q, full, sg.w0 * HD, sg.h0, p + 1, sg.b);
   if (COMPOSE) tma_load_4d(sbase + C::OFF_F + fslot * C::F_STRIDE, tm_f, full, sg.w0 - 4, sg.h0 - 1, p, sg.b * 3);
-  return pseg;
 }
 
 template <int TH, int NS, bool COMPOSE>
-__device__ __forceinline__ int try_issue2(uint32_t sbase, const Seg* __restrict__ segs, int pseg, int total_stages,
-                                          const CUtensorMap* tm_k, const CUtensorMap* tm_q, const CUtensorMap* tm_f) {
+__device__ __forceinline__ void try_issue2(uint32_t sbase, const Seg* __restrict__ segs, int total_stages,
+                                           const CUtensorMap* tm_k, const CUtensorMap* tm_q, const CUtensorMap* tm_f) {
   using C = Cfg2<TH, NS>;
   const uint32_t next_addr = sbase + C::OFF_NEXT;
   const uint32_t n = lds_volatile(next_addr);
   if ((int)n < total_stages) {
     const uint32_t k = n / NS;
     if (mbar_test(sbase + C::OFF_CNT + 8 * (n - k * NS), (k - 1) & 1u)) {
-      if (atom_cas_relaxed(next_addr, n, n + 1) == n)
-        pseg = issue_stage2<TH, NS, COMPOSE>(sbase, segs, pseg, (int)n, tm_k, tm_q, tm_f);
+      if (atom_cas_relaxed(next_addr, n, n + 1) == n) issue_stage2<TH, NS, COMPOSE>(sbase, segs, (int)n, tm_k, tm_q, tm_f);
     }
   }
-  return pseg;
 }
 
 // Fold the three logit pairs of one key-row combination into the running state of a voxel pair.  The update is the same
@@ -237,8 +241,16 @@ __device__ __forceinline__ void reset_acc(Acc2& A) {
   A.m = pk(-1e30f, -1e30f);
 }
 
+__device__ __forceinline__ float ldg_pred(const float* p, bool pr) {
+  float v;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@p ld.global.nc.f32 %0, [%1];\n\t}"
+      : "=f"(v)
+      : "l"(p), "r"((int)pr));
+  return v;
+}
+
 // The marching loop of one CTA.  SAFE selects the online-maximum softmax.
-template <int TH, int NS, bool COMPOSE, bool MOVED, bool SAFE>
+template <int TH, int NS, bool COMPOSE, bool MOVED, bool SAFE, int VAR>
 __device__ __forceinline__ void march(uint8_t* smem, const CUtensorMap* tm_k, const CUtensorMap* tm_q, const CUtensorMap* tm_f,
                                       const float* __restrict__ flow_in, const float* __restrict__ moving,
                                       float* __restrict__ out0, float* __restrict__ moved, const Dims2& dm, float qscale,
@@ -256,13 +268,21 @@ __device__ __forceinline__ void march(uint8_t* smem, const CUtensorMap* tm_k, co
   const int N = D * HW;
   const float ndm1 = -dm.dm1, nhm1 = -dm.hm1, nwm1 = -dm.wm1;
 
-  int pseg = 0;
   if (tid == 0) {
-    for (int n = 0; n < NS && n < total_stages; ++n) pseg = issue_stage2<TH, NS, COMPOSE>(sbase, segs, pseg, n, tm_k, tm_q, tm_f);
+    for (int n = 0; n < NS && n < total_stages; ++n) issue_stage2<TH, NS, COMPOSE>(sbase, segs, n, tm_k, tm_q, tm_f);
   }
 
   int slot = 0, fslot = 0;
   uint32_t par = 0;
+  // wait for a "full" barrier; a warp that has to wait keeps offering to issue the next stage
+  auto wait_full = [&](uint32_t bar, uint32_t parity) {
+    if (!mbar_try_wait_hint(bar, parity, 200)) {
+      do {
+        if (lane == 0) try_issue2<TH, NS, COMPOSE>(sbase, segs, total_stages, tm_k, tm_q, tm_f);
+        __syncwarp();
+      } while (!mbar_try_wait_hint(bar, parity, 200));
+    }
+  };
   const uint8_t* q_thr = smem + C::OFF_Q + ((2 * r) * TW + lane) * (HD * 4);
   const uint8_t* k_thr = smem + C::OFF_K + ((2 * r) * KW + lane + KOFF) * (HD * 4);
   const uint8_t* f_thr = smem + C::OFF_F + ((2 * r) * FWP + lane + FOFF) * 4;
@@ -297,7 +317,7 @@ __device__ __forceinline__ void march(uint8_t* smem, const CUtensorMap* tm_k, co
 #pragma unroll 1
     for (int z = 0; z <= nsteps; ++z) {
       {
-        if (lane == 0) pseg = try_issue2<TH, NS, COMPOSE>(sbase, segs, pseg, total_stages, tm_k, tm_q, tm_f);
+        if (lane == 0) try_issue2<TH, NS, COMPOSE>(sbase, segs, total_stages, tm_k, tm_q, tm_f);
         __syncwarp();
         p2 mv[8];           // moved-image corners (A, B): z0y0x0 z0y0x1 z0y1x0 z0y1x1 z1y0x0 ...
         p2 mfx = 0, mfy = 0, mfz = 0;
@@ -397,11 +417,45 @@ __device__ __forceinline__ void march(uint8_t* smem, const CUtensorMap* tm_k, co
               floor_magic(hi(mz), jzB, zfB);
               floor_magic(hi(my), jyB, yfB);
               floor_magic(hi(mx), jxB, xfB);
+              // VAR bit 2: zero padding is part of the straight path -- every corner is a predicated load whose predicate is
+              // "inside the volume", whatever the sample position.  Before, a warp with ONE lane sampling across a face of
+              // the volume took the slow path below with all its lanes; the CTAs that own border rows / columns / planes
+              // were the last to finish and the average SM was busy for 77 % of the kernel (ncu sm__cycles_active avg vs
+              // max, profiles/r04a).  Only coordinates outside floor_magic's exact range (|c| >= 2^22, NaN) still leave.
+              constexpr bool XIN = (VAR & 4) != 0;
               const bool intA = validA && ((unsigned)jzA < (unsigned)(D - 1)) && ((unsigned)jyA < (unsigned)(H - 1)) &&
                                 ((unsigned)jxA < (unsigned)(W - 1));
               const bool intB = validB && ((unsigned)jzB < (unsigned)(D - 1)) && ((unsigned)jyB < (unsigned)(H - 1)) &&
                                 ((unsigned)jxB < (unsigned)(W - 1));
-              if (__all_sync(0xffffffffu, intA && intB)) {
+              const bool tame = (fabsf(lo(mz)) < 4.0e6f) && (fabsf(lo(my)) < 4.0e6f) && (fabsf(lo(mx)) < 4.0e6f) &&
+                                (fabsf(hi(mz)) < 4.0e6f) && (fabsf(hi(my)) < 4.0e6f) && (fabsf(hi(mx)) < 4.0e6f);
+              if (XIN && __all_sync(0xffffffffu, tame)) {
+                mfz = psub(mz, pk(zfA, zfB));
+                mfy = psub(my, pk(yfA, yfB));
+                mfx = psub(mx, pk(xfA, xfB));
+                const bool z0A = validA && ((unsigned)jzA < (unsigned)D), z1A = validA && ((unsigned)(jzA + 1) < (unsigned)D);
+                const bool z0B = validB && ((unsigned)jzB < (unsigned)D), z1B = validB && ((unsigned)(jzB + 1) < (unsigned)D);
+                const bool y0A = (unsigned)jyA < (unsigned)H, y1A = (unsigned)(jyA + 1) < (unsigned)H;
+                const bool y0B = (unsigned)jyB < (unsigned)H, y1B = (unsigned)(jyB + 1) < (unsigned)H;
+                const bool x0A = (unsigned)jxA < (unsigned)W, x1A = (unsigned)(jxA + 1) < (unsigned)W;
+                const bool x0B = (unsigned)jxB < (unsigned)W, x1B = (unsigned)(jxB + 1) < (unsigned)W;
+                // signed element offsets: corners outside the volume form addresses that are never dereferenced
+                // (|offset| < 2^31 because |j| < 2^22 here and B * N < 2^31)
+                const int iA = (int)(boff1 + (((unsigned)jzA * (unsigned)H + (unsigned)jyA) * (unsigned)W + (unsigned)jxA));
+                const int iB = (int)(boff1 + (((unsigned)jzB * (unsigned)H + (unsigned)jyB) * (unsigned)W + (unsigned)jxB));
+                const float *pA0 = moving + (ptrdiff_t)iA, *pA1 = moving + (ptrdiff_t)(iA + W),
+                            *pA2 = moving + (ptrdiff_t)(iA + HW), *pA3 = moving + (ptrdiff_t)(iA + HW + W);
+                const float *pB0 = moving + (ptrdiff_t)iB, *pB1 = moving + (ptrdiff_t)(iB + W),
+                            *pB2 = moving + (ptrdiff_t)(iB + HW), *pB3 = moving + (ptrdiff_t)(iB + HW + W);
+                mv[0] = pk(ldg_pred(pA0, z0A && y0A && x0A), ldg_pred(pB0, z0B && y0B && x0B));
+                mv[1] = pk(ldg_pred(pA0 + 1, z0A && y0A && x1A), ldg_pred(pB0 + 1, z0B && y0B && x1B));
+                mv[2] = pk(ldg_pred(pA1, z0A && y1A && x0A), ldg_pred(pB1, z0B && y1B && x0B));
+                mv[3] = pk(ldg_pred(pA1 + 1, z0A && y1A && x1A), ldg_pred(pB1 + 1, z0B && y1B && x1B));
+                mv[4] = pk(ldg_pred(pA2, z1A && y0A && x0A), ldg_pred(pB2, z1B && y0B && x0B));
+                mv[5] = pk(ldg_pred(pA2 + 1, z1A && y0A && x1A), ldg_pred(pB2 + 1, z1B && y0B && x1B));
+                mv[6] = pk(ldg_pred(pA3, z1A && y1A && x0A), ldg_pred(pB3, z1B && y1B && x0B));
+                mv[7] = pk(ldg_pred(pA3 + 1, z1A && y1A && x1A), ldg_pred(pB3 + 1, z1B && y1B && x1B));
+              } else if (!XIN && __all_sync(0xffffffffu, intA && intB)) {
                 mfz = psub(mz, pk(zfA, zfB));
                 mfy = psub(my, pk(yfA, yfB));
                 mfx = psub(mx, pk(xfA, xfB));
@@ -434,12 +488,7 @@ __device__ __forceinline__ void march(uint8_t* smem, const CUtensorMap* tm_k, co
 
         // ---- (2) key plane of this iteration
         if (z < nsteps) {
-          if (!mbar_try_wait_hint(bar_full + 8 * slot, par, 200)) {
-            do {
-              if (lane == 0) pseg = try_issue2<TH, NS, COMPOSE>(sbase, segs, pseg, total_stages, tm_k, tm_q, tm_f);
-              __syncwarp();
-            } while (!mbar_try_wait_hint(bar_full + 8 * slot, par, 200));
-          }
+          wait_full(bar_full + 8 * slot, par);
           {   // queries of the new pair into slot j (uniform branch on the phase: the loads target the slot's registers)
             const p2* qa = reinterpret_cast<const p2*>(q_thr + slot * C::Q_STRIDE);
             const p2* qb = reinterpret_cast<const p2*>(q_thr + slot * C::Q_STRIDE + TW * HD * 4);
@@ -588,10 +637,12 @@ __device__ __forceinline__ void march(uint8_t* smem, const CUtensorMap* tm_k, co
   }
 }
 
-template <int TH, int NS, bool COMPOSE, bool MOVED>
+
+template <int TH, int NS, bool COMPOSE, bool MOVED, int VAR>
 __global__ void __launch_bounds__(TH * 32, 1)
 fused_march2_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_q,
-                    const __grid_constant__ CUtensorMap tm_f, const float* __restrict__ rpb,
+                    const __grid_constant__ CUtensorMap tm_f, const __grid_constant__ UnitTable tab,
+                    const float* __restrict__ rpb,
                     const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta,
                     const float* __restrict__ flow_in, const float* __restrict__ moving, float* __restrict__ out0,
                     float* __restrict__ moved, const Dims2 dm, float scale, float post, int Cmov, int force_safe, int four) {
@@ -611,9 +662,7 @@ fused_march2_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
     // 128-byte lines their halos share (a 160-byte flow row spans three) come from DRAM once and from L2 afterwards
     // (measured: 492 -> see profiles/r03*_fused_v2_full.txt MB read per launch).
     const int g = blockIdx.x / dm.group, m = blockIdx.x - g * dm.group;
-    const long long u_begin = (long long)g * dm.units_per_cta;
-    long long u_end = u_begin + dm.units_per_cta;
-    if (u_end > dm.total_units) u_end = dm.total_units;
+    const long long u_begin = tab.u[g], u_end = tab.u[g + 1];
     int ns = 0, stage = 0;
     long long u = u_begin;
     while (u < u_end && ns < MAXSEG) {
@@ -675,11 +724,11 @@ fused_march2_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
   const int total_stages = segs[nseg].s_begin;
   const float qscale = scale * kLog2e;
   if (*s_fast)
-    march<TH, NS, COMPOSE, MOVED, false>(smem, &tm_k, &tm_q, &tm_f, flow_in, moving, out0, moved, dm, qscale, post, Cmov, nseg,
-                                         total_stages, four);
+    march<TH, NS, COMPOSE, MOVED, false, VAR>(smem, &tm_k, &tm_q, &tm_f, flow_in, moving, out0, moved, dm, qscale, post, Cmov, nseg,
+                                              total_stages, four);
   else
-    march<TH, NS, COMPOSE, MOVED, true>(smem, &tm_k, &tm_q, &tm_f, flow_in, moving, out0, moved, dm, qscale, post, Cmov, nseg,
-                                        total_stages, four);
+    march<TH, NS, COMPOSE, MOVED, true, VAR>(smem, &tm_k, &tm_q, &tm_f, flow_in, moving, out0, moved, dm, qscale, post, Cmov, nseg,
+                                             total_stages, four);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -716,26 +765,49 @@ bool encode4b(CUtensorMap* map, const void* base, const cuuint64_t (&dims)[4], c
   return true;
 }
 
-template <int TH, int NS, bool COMPOSE, bool MOVED>
-int launch_cfg2(const CUtensorMap& mk, const CUtensorMap& mq, const CUtensorMap& mf, const float* rpb, const float* g,
-                const float* bta, const float* flow_in, const float* moving, float* out0, float* moved, const Dims2& dm,
-                int grid, float scale, float post, int Cmov, int force_safe, cudaStream_t st) {
+// Step-balanced partition of the (row band, plane) units over at most `maxg` CTA groups: every group gets a budget of T
+// steps, a segment of L planes costs L + 2.  Returns the number of groups used (maxg + 1: does not fit).
+int partition_units(long long total, int D, int T, int maxg, int* u) {
+  long long pos = 0;
+  int g = 0;
+  u[0] = 0;
+  while (pos < total) {
+    if (g == maxg) return maxg + 1;
+    int budget = T, nseg = 0;
+    while (pos < total && budget >= 3 && nseg < MAXSEG - 1) {
+      const long long band_end = (pos / D + 1) * D;
+      long long L = band_end - pos;
+      if (L > budget - 2) L = budget - 2;
+      if (L > total - pos) L = total - pos;
+      pos += L;
+      budget -= (int)L + 2;
+      ++nseg;
+    }
+    u[++g] = (int)pos;
+  }
+  return g;
+}
+
+template <int TH, int NS, bool COMPOSE, bool MOVED, int VAR>
+int launch_cfg2(const CUtensorMap& mk, const CUtensorMap& mq, const CUtensorMap& mf, const UnitTable& tab, const float* rpb,
+                const float* g, const float* bta, const float* flow_in, const float* moving, float* out0, float* moved,
+                const Dims2& dm, int grid, float scale, float post, int Cmov, int force_safe, cudaStream_t st) {
   using C = Cfg2<TH, NS>;
-  auto kern = fused_march2_kernel<TH, NS, COMPOSE, MOVED>;
+  auto kern = fused_march2_kernel<TH, NS, COMPOSE, MOVED, VAR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
   if (e != cudaSuccess) {
     set_error("modet_fused(TMA v2): cannot reserve %d B of shared memory: %s", C::SMEM, cudaGetErrorString(e));
     return SMILE_ERR_CUDA;
   }
-  kern<<<grid, C::THREADS, C::SMEM, st>>>(mk, mq, mf, rpb, g, bta, flow_in, moving, out0, moved, dm, scale, post, Cmov,
+  kern<<<grid, C::THREADS, C::SMEM, st>>>(mk, mq, mf, tab, rpb, g, bta, flow_in, moving, out0, moved, dm, scale, post, Cmov,
                                           force_safe, 4);
   return check_launch("modet_fused(TMA v2)");
 }
 
-template <int TH, int NS>
+template <int TH, int NS, int VAR>
 int launch_tiles2(const float* q, const float* k, const float* rpb, const float* g, const float* bta, const float* flow_in,
                   const float* moving, float* w_out, float* flow_out, float* moved, int B, int D, int H, int W, float scale,
-                  float post, int Cmov, int force_safe, cudaStream_t st) {
+                  float post, int Cmov, int force_safe, cudaStream_t st, bool* handled) {
   using C = Cfg2<TH, NS>;
   const bool compose = flow_in != nullptr;
   Dims2 dm;
@@ -744,13 +816,27 @@ int launch_tiles2(const float* q, const float* k, const float* rpb, const float*
   dm.ncol_w = ceil_div(W, TW);
   dm.group = dm.ncol_w;
   dm.total_units = (long long)B * dm.ncol_h * D;
-  int groups = kNumSMs / dm.group;                      // one CTA per SM: all groups are co-resident
-  if (groups < 1) groups = 1;                           // very wide volumes: more than one wave (still correct)
-  long long per = ceil_div_ll(dm.total_units, (long long)groups);
-  if (per < 4) per = 4;
-  if (per > (long long)(MAXSEG - 2) * D) per = (long long)(MAXSEG - 2) * D;
-  dm.units_per_cta = (int)per;
-  const int grid = (int)ceil_div_ll(dm.total_units, per) * dm.group;
+  if (dm.total_units >= (1LL << 31)) return SMILE_OK;   // not handled: generic kernel
+  // One CTA per SM and all groups co-resident when the volume allows it; wider / longer volumes take more groups (more
+  // than one wave, still correct) up to the size of the table.
+  int groups = kNumSMs / dm.group;
+  if (groups < 1) groups = 1;
+  UnitTable tab;
+  const int t_cap = (MAXSEG - 2) * D;
+  int T = (int)ceil_div_ll(dm.total_units, (long long)groups) + 2, used = 0;
+  if (T < 3) T = 3;
+  for (;; ++T) {
+    if (T > t_cap) {
+      T = t_cap;
+      groups = kNumSMs;
+    }
+    used = partition_units(dm.total_units, D, T, groups, tab.u);
+    if (used <= groups) break;
+    if (T == t_cap) return SMILE_OK;                     // does not fit the table: generic kernel
+  }
+  for (int i = used + 1; i <= kNumSMs; ++i) tab.u[i] = tab.u[used];
+  const int grid = used * dm.group;
+  *handled = true;
   dm.dm1 = (float)(D - 1); dm.hm1 = (float)(H - 1); dm.wm1 = (float)(W - 1);
   dm.rd = 1.0f / dm.dm1; dm.rh = 1.0f / dm.hm1; dm.rw = 1.0f / dm.wm1;
 
@@ -771,13 +857,13 @@ int launch_tiles2(const float* q, const float* k, const float* rpb, const float*
     mf = mq;
   }
   if (!compose)
-    return launch_cfg2<TH, NS, false, false>(mk, mq, mf, rpb, g, bta, nullptr, nullptr, w_out, nullptr, dm, grid, scale, 1.0f,
-                                             0, force_safe, st);
+    return launch_cfg2<TH, NS, false, false, VAR>(mk, mq, mf, tab, rpb, g, bta, nullptr, nullptr, w_out, nullptr, dm, grid, scale,
+                                                  1.0f, 0, force_safe, st);
   if (moved != nullptr)
-    return launch_cfg2<TH, NS, true, true>(mk, mq, mf, rpb, g, bta, flow_in, moving, flow_out, moved, dm, grid, scale, post,
-                                           Cmov, force_safe, st);
-  return launch_cfg2<TH, NS, true, false>(mk, mq, mf, rpb, g, bta, flow_in, nullptr, flow_out, nullptr, dm, grid, scale, post,
-                                          0, force_safe, st);
+    return launch_cfg2<TH, NS, true, true, VAR>(mk, mq, mf, tab, rpb, g, bta, flow_in, moving, flow_out, moved, dm, grid, scale,
+                                                post, Cmov, force_safe, st);
+  return launch_cfg2<TH, NS, true, false, VAR>(mk, mq, mf, tab, rpb, g, bta, flow_in, nullptr, flow_out, nullptr, dm, grid, scale,
+                                               post, 0, force_safe, st);
 }
 
 }  // namespace
@@ -794,14 +880,17 @@ int launch_modet_attn_tma2(const float* q, const float* k, const float* rpb, con
   if ((long long)D * H * W * HD >= (1LL << 31)) return SMILE_OK;
   if ((long long)B * 3 * D * H * W >= (1LL << 32)) return SMILE_OK;   // 32-bit element offsets inside the kernel
   if (get_encode2() == nullptr) return SMILE_OK;
-  *handled = true;
+  // SMILE_FUSED_V2: bit 0 = online-maximum softmax even when the bound allows the fast loop (profiling / test knob);
+  // bit 2 = the round-3 border handling (whole-warp slow path at the faces of the volume) for A/B runs
   static const int variant = [] { const char* e = getenv("SMILE_FUSED_V2"); return e ? atoi(e) : 0; }();
-  const int force_safe = (variant & 1);        // profiling / test knob: online-maximum softmax even when the bound allows
-  if (variant & 2)                             // 8 warps: 16-row tiles
-    return launch_tiles2<8, 3>(q, k, rpb, ln_gamma, ln_beta, flow_in, moving, w_out, flow_out, moved, B, D, H, W, scale, post,
-                               Cmov, force_safe, st);
-  return launch_tiles2<12, 3>(q, k, rpb, ln_gamma, ln_beta, flow_in, moving, w_out, flow_out, moved, B, D, H, W, scale, post,
-                              Cmov, force_safe, st);
+  const int force_safe = (variant & 1);
+  const int var = (variant & 4) ? 0 : 4;
+#define SMILE_GO(V)                                                                                                       \
+  return launch_tiles2<12, 3, V>(q, k, rpb, ln_gamma, ln_beta, flow_in, moving, w_out, flow_out, moved, B, D, H, W, scale, \
+                                 post, Cmov, force_safe, st, handled)
+  if (var == 4) SMILE_GO(4);
+  SMILE_GO(0);
+#undef SMILE_GO
 }
 
 }  // namespace smile

@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 ) 
+python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/job16_bench.json 2> gpurun_out/job16_bench.err
+python - <<'PY'
+import json
+try:
+    d=json.loads(open('gpurun_out/job16_bench.json').read().strip().splitlines()[-1])
+    print('value', d['value'], 'ms', d['ms_per_step'], 'launches', d['gpu_launches'])
+    print('e2e', json.dumps(d['e2e'])[:300])
+    print('roofline', json.dumps(d['roofline']))
+    print('train', d.get('train',{}).get('ms_per_step'), 'train_bf16', d.get('train_bf16',{}).get('ms_per_step'))
+except Exception as e:
+    print('bench failed', e); print(open('gpurun_out/job16_bench.err').read()[-2500:])
+PY

@@ -214,6 +214,12 @@ int launch_conv3d(const float* in, const float* weight, const float* bias, float
                   double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
                   cudaStream_t st, const float* wprep) {
   {
+    // the wide 8-channel layers: fp16-split tensor-core kernel with fp32-class accuracy (conv_march.cu)
+    bool split = false;
+    int rc = launch_conv3d_march_split(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st, &split);
+    if (split) return rc;
+  }
+  {
     // layers wide enough for an MMA (>= 12 output channels) run on the tensor cores (conv_tc.cu); SMILE_CONV_TC=0
     // keeps everything on the SIMT kernels
     bool tc = false;

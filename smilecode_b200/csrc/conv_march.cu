@@ -15,6 +15,7 @@
 //   * InstanceNorm statistics of the raw output are kept in registers for the whole march and reduced once.
 // Contract identical to smile_conv3d_bf16_fwd (NCDHW fp32 in / out, normalise-on-load, fp64 statistics).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstdint>
 #include <cstdlib>
@@ -35,7 +36,7 @@ constexpr int PLANE_POS = 592;        // staged positions per plane (18 * 32 = 5
 constexpr int PLANE_BYTES = 2 * PLANE_POS * 16;   // two channel blocks of 8 bf16
 constexpr int RING = 4;
 constexpr int NT = 16;                // output channels (UMMA N)
-constexpr int B_BYTES = 27 * 2 * NT * 16;
+constexpr int B_BYTES = 32 * 2 * NT * 16;   // 27 taps (bf16, Cin > 8), 15 tap pairs (bf16, Cin <= 8), 2 x 15 + a zero block (fp16 split)
 constexpr int WORKERS = 256;          // warps 0-7 stage the planes and drain the accumulators
 constexpr int THREADS = WORKERS + 32; // warp 8 only issues the MMAs (one lane): 108 per plane would otherwise delay warp 0
 constexpr int OFF_B = RING * PLANE_BYTES;
@@ -106,13 +107,71 @@ __global__ void conv_march_prep_kernel(const float* __restrict__ w, __nv_bfloat1
   wprep[e] = __float2bfloat16_rn(v);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// SPLIT mode: fp32-class accuracy on the tensor cores for the layers with at most 8 input and 8 output channels.
+// Every operand is written x = hi + 2^-11 * lo with hi = fp16(x), lo = fp16((x - hi) * 2^11): 22 significant bits, the
+// same class as the three-product TF32 split of conv_tc.cu, but with K = 16 per MMA and two taps per MMA.  Per tap pair
+// two MMAs into a 24-column accumulator [ hh_a | corr | hh_b ]:
+//     even pairs   A_hi x [ W_hi | W_lo ] at column 0      hh_a += hi*hi      corr += hi*lo
+//     odd pairs    A_hi x [ W_lo | W_hi ] at column 8      corr += hi*lo      hh_b += hi*hi
+//     every pair   A_lo x [  0   | W_hi ] at column 0                         corr += lo*hi
+// and the epilogue returns (hh_a[n] + hh_b[n]) + 2^-11 * corr[n].  Products of two fp16 values are exact in fp32; what
+// costs accuracy is the accumulation in TMEM (truncating adds, error ~ linear in the number of accumulated MMAs,
+// tools/probe/tf32x3_probe.cu), so the leading term is spread over two chains of 8 and 7 MMAs that are added with a
+// round-to-nearest fp32 add; the corrections are 2^-11 smaller and can share one column group.  One MMA against a zero
+// B block (N = 32, accumulate off) clears the 32 columns of an M tile first: the chains overlap in `corr`, so no single
+// MMA could be the "first" for all of its columns.
+// |x| must stay below the fp16 range (65504) after the normalise-on-load: operands are clamped there.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((a - hf.x) * 2048.f, (b - hf.y) * 2048.f);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// weight [Cout <= 8][Cin <= 8][27] fp32 -> fp16 B operands [set 2][mma 15][cb 2][NT 16][8] + two all-zero blocks:
+//   set 0, even pair: rows n < 8 = W_hi[n], rows n >= 8 = W_lo[n - 8];  odd pair: the two halves swapped
+//   set 1: rows n < 8 = 0, rows n >= 8 = W_hi[n - 8]
+__global__ void conv_march_prep_split_kernel(const float* __restrict__ w, __half* __restrict__ wprep, int Cout, int Cin) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 32 * 2 * NT * 8) return;
+  if (e >= 30 * 2 * NT * 8) {
+    wprep[e] = __float2half_rn(0.f);
+    return;
+  }
+  int t = e;
+  const int j = t % 8; t /= 8;
+  const int n = t % NT; t /= NT;
+  const int cb = t % 2; t /= 2;
+  const int set = t / 15, i = t % 15;
+  const int t0 = pair_first_tap(i);
+  const bool single = (i % 5) == 4;
+  const int tap = t0 + cb, co = n & 7;
+  float v = 0.f;
+  if (!(single && cb == 1) && j < Cin && co < Cout) v = w[((long long)co * Cin + j) * 27 + tap];
+  v = fminf(fmaxf(v, -65504.f), 65504.f);
+  const __half h = __float2half_rn(v);
+  const __half l = __float2half_rn((v - __half2float(h)) * 2048.f);
+  __half r = __float2half_rn(0.f);
+  if (set == 0) r = ((n < 8) != ((i & 1) != 0)) ? h : l;
+  else if (n >= 8) r = h;
+  wprep[e] = r;
+}
+
 // CIN8: at most 8 input channels (the second channel block stays zero); NORM: InstanceNorm + LeakyReLU on load
-template <bool CIN8, bool NORM>
+// SPLIT (with CIN8, Cout <= 8): fp16 hi / lo operands, see above; the second channel-block plane of a ring slot holds A_lo
+template <bool CIN8, bool NORM, bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 2)
-conv_march_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict__ wprep, const float* __restrict__ bias,
+conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, const float* __restrict__ bias,
                   float* __restrict__ out, const double* __restrict__ in_stats, double* __restrict__ out_stats, int Cin,
                   int Cout, int D, int H, int W, int ntr, int ntc, int DS, int act_out, float eps) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int MCOLS = SPLIT ? 32 : NT;        // TMEM columns per M tile
+  constexpr int TCOLS = 2 * MT * MCOLS;         // two accumulator buffers: 128 columns (bf16) or 256 (split)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
   float* s_mr = reinterpret_cast<float*>(smem + OFF_MR);
@@ -139,7 +198,7 @@ conv_march_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict_
     bulk_g2s(smem_u32(smem + OFF_B), wprep, B_BYTES, smem_u32(bars));
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TCOLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid < 16) {
@@ -154,6 +213,7 @@ conv_march_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict_
     s_mr[2 * tid] = rstd;
     s_mr[2 * tid + 1] = shift;
   }
+  for (int i = tid; i < 8 * NT * 2; i += THREADS) s_red[i] = 0.0;
   // zero the ring once: the unused channel block, the overhang and the out-of-volume positions stay zero
   for (int i = tid; i < RING * PLANE_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -163,7 +223,7 @@ conv_march_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict_
 
   const float* inb = in + (long long)b * Cin * N;
   constexpr int NCH = CIN8 ? 8 : 16;
-  constexpr int PB = (CIN8 ? 1 : 2) * PLANE_POS * 16;     // bytes of one staged plane (one or two channel blocks)
+  constexpr int PB = ((CIN8 && !SPLIT) ? 1 : 2) * PLANE_POS * 16;     // bytes of one staged plane (one or two blocks)
 
   // ---- stage one input plane (global depth dd) into its ring slot
   auto stage_plane = [&](int dd) {
@@ -192,6 +252,16 @@ conv_march_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict_
 #pragma unroll
         for (int j = 0; j < NCH; ++j) v[j] = 0.f;
       }
+      if (SPLIT) {
+        uint4 hi4, lo4;
+        split_pair(v[0], v[1], hi4.x, lo4.x);
+        split_pair(v[2], v[3], hi4.y, lo4.y);
+        split_pair(v[4], v[5], hi4.z, lo4.z);
+        split_pair(v[6], v[7], hi4.w, lo4.w);
+        slot[i] = hi4;
+        slot[PLANE_POS + i] = lo4;
+        continue;
+      }
       slot[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
       if (!CIN8)
         slot[PLANE_POS + i] =
@@ -206,17 +276,44 @@ conv_march_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict_
   float* s_bias = s_mr + 32;
   if (tid < NT) s_bias[tid] = (tid < Cout) ? __ldg(bias + tid) : 0.f;
   __syncthreads();
+  // InstanceNorm statistics of the raw output: fp32 partial sums per thread, flushed every four planes through a warp
+  // reduction into per-warp fp64 accumulators in shared memory.  (Keeping the fp32 partials for the whole march -- up to
+  // 2 x D/DS values per thread, 2560 per warp -- cost 1e-6 relative on the variance of a whole channel: a coherent error
+  // that the 5-level cascade amplifies; with the fp16-split operands it alone moved the full-size flow error from 1.06x
+  // to 1.75x the reference's own fp32 error.)
   float st_s[NT], st_q[NT];
 #pragma unroll
   for (int n = 0; n < NT; ++n) st_s[n] = st_q[n] = 0.f;
+  auto flush_stats = [&]() {
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      if (n >= Cout) break;
+      float sv = st_s[n], sq = st_q[n];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      }
+      if (lane == 0) {
+        s_red[(warp * NT + n) * 2] += (double)sv;
+        s_red[(warp * NT + n) * 2 + 1] += (double)sq;
+      }
+      st_s[n] = st_q[n] = 0.f;
+    }
+  };
 
   auto drain_plane = [&](int dd, int buf) {
 #pragma unroll
     for (int mm = 0; mm < 2; ++mm) {
       const int m = mbase + mm;
       const int h = h0 + 4 * m + q;
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * (MT * NT) + m * NT);
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * (MT * MCOLS) + m * MCOLS);
       uint32_t r[16];
+      uint32_t r2[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      if (SPLIT)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7])
+                     : "r"(taddr + 16u));
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
           : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -227,8 +324,10 @@ conv_march_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict_
         float* ob = out + (long long)b * Cout * N + (long long)dd * HW + h * W + (w0 + lane);
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
-          if (n < Cout) {
-            const float val = __uint_as_float(r[n]) + s_bias[n];
+          if (n < Cout && (!SPLIT || n < 8)) {
+            const float val = (SPLIT ? fmaf(__uint_as_float(r[(n + 8) & 15]), 1.f / 2048.f,
+                                            __fadd_rn(__uint_as_float(r[n]), __uint_as_float(r2[n & 7])))
+                                     : __uint_as_float(r[n])) + s_bias[n];
             ob[(long long)n * N] = act_out ? lrelu01(val) : val;
             st_s[n] += val;
             st_q[n] = fmaf(val, val, st_q[n]);
@@ -238,7 +337,9 @@ conv_march_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict_
     }
   };
 
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // instruction descriptor: fp32 accumulate; A and B formats bf16 (1) or, in SPLIT mode, fp16 (0); N = 16, M = 128
+  const uint32_t idesc = (1u << 4) | (SPLIT ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t idesc32 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(32 >> 3) << 17);   // the same with N = 32
   const uint32_t ring_base = smem_u32(smem), b_base = smem_u32(smem + OFF_B);
 
   auto arrive = [&](int bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bars + bar)) : "memory"); };
@@ -261,6 +362,7 @@ conv_march_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict_
         drain_plane(d - 1, pb);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         arrive(5 + pb);                                              // TMEM buffer pb may be overwritten
+        if (((d - d0) & 3) == 0) flush_stats();
       }
     }
     {
@@ -268,6 +370,7 @@ conv_march_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict_
       mbar_wait(smem_u32(bars + 1 + pb), ph[pb]);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       drain_plane(d1 - 1, pb);
+      flush_stats();
     }
   } else if (lane == 0) {
     // ---------------- issuer: 4 x 27 MMAs per plane
@@ -297,7 +400,7 @@ conv_march_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict_
                  ::"r"(DCOL), "l"(DA), "l"(DB), "r"(idesc) : "memory");
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
-        const uint32_t dcol = tmem + (uint32_t)(par * (MT * NT) + m * NT);
+        const uint32_t dcol = tmem + (uint32_t)(par * (MT * MCOLS) + m * MCOLS);
         if (CIN8) {
           const uint64_t da_row = make_desc(0u, 16, 128), da_wrap = make_desc(0u, (P - 2) * 16, 128);
 #pragma unroll
@@ -308,6 +411,17 @@ conv_march_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict_
             const uint64_t hi = (kw == 2 && t0 != 8) ? da_wrap : da_row;   // the lone ninth tap: zero weights on chunk 2
             const uint64_t da = hi + (uint64_t)(slot16[kd] + (uint32_t)(m * 128 + kh * P + kw));
             const uint64_t db = db0 + (uint64_t)(i * 2 * NT);
+            if (SPLIT) {
+              if (i == 0) {   // clear the 32 columns of this M tile: any A x the zero block (N = 32), accumulate off
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                             ::"r"(dcol), "l"(da), "l"(make_desc(b_base + 30 * 2 * NT * 16, 2 * NT * 16, 128)), "r"(idesc32) : "memory");
+              }
+              // even pair: [W_hi | W_lo] -> hh_a, corr;  odd pair: [W_lo | W_hi] at column 8 -> corr, hh_b
+              SMILE_MMA(dcol + ((i & 1) ? 8u : 0u), da, db, false)
+              // A_lo (second block of the slot) x [0 | W_hi] (second set of B blocks) -> corr
+              SMILE_MMA(dcol, da + (uint64_t)PLANE_POS, db + (uint64_t)(15 * 2 * NT), false)
+              continue;
+            }
             SMILE_MMA(dcol, da, db, i == 0)
           }
         } else {
@@ -328,24 +442,10 @@ conv_march_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(128));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TCOLS));
 
-  // ---- InstanceNorm statistics: warp shuffle -> shared -> one fp64 atomic per channel and CTA
+  // ---- InstanceNorm statistics: per-warp fp64 sums (flush_stats) -> one fp64 atomic per channel and CTA
   if (out_stats != nullptr) {
-#pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      if (warp >= 8) break;
-      float s = st_s[n], sq = st_q[n];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        sq += __shfl_xor_sync(0xffffffffu, sq, o);
-      }
-      if (lane == 0) {
-        s_red[(warp * NT + n) * 2] = (double)s;
-        s_red[(warp * NT + n) * 2 + 1] = (double)sq;
-      }
-    }
     __syncthreads();
     if (tid < 2 * NT) {
       const int n = tid >> 1, which = tid & 1;
@@ -361,13 +461,11 @@ conv_march_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict_
 
 }  // namespace
 
-// Depth-marching bf16 tensor-core conv for Cin <= 16 and Cout <= 16.  *handled = false otherwise.
-int launch_conv3d_march_bf16(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
-                             double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
-                             cudaStream_t st, bool* handled) {
-  *handled = false;
-  if (Cin < 2 || Cin > 16 || Cout > 16 || D < 1 || H < 2 || W < 2) return SMILE_OK;
-  *handled = true;
+namespace {
+// common launch path of the two precisions
+int launch_march(bool split, const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
+                 double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps, cudaStream_t st) {
+  const char* what = split ? "conv3d(fp16-split march)" : "conv3d(bf16 march)";
   const int ntr = ceil_div(H, TR), ntc = ceil_div(W, TC);
   const long long tiles = (long long)B * ntr * ntc;
   // Two CTAs per SM (92 KB of shared memory, 128 TMEM columns each): while one stages / drains, the other's MMAs run.
@@ -388,30 +486,62 @@ int launch_conv3d_march_bf16(const float* in, const float* weight, const float* 
       if (cur < want) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &want);
     }
   });
-  __nv_bfloat16* wprep = nullptr;
-  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&wprep), B_BYTES, st);
+  void* wprep = nullptr;
+  cudaError_t e = cudaMallocAsync(&wprep, B_BYTES, st);
   if (e != cudaSuccess) {
-    set_error("conv3d(bf16 march): cudaMallocAsync failed: %s", cudaGetErrorString(e));
+    set_error("%s: cudaMallocAsync failed: %s", what, cudaGetErrorString(e));
     return SMILE_ERR_CUDA;
   }
-  conv_march_prep_kernel<<<ceil_div(27 * 2 * NT * 8, 256), 256, 0, st>>>(weight, wprep, Cout, Cin);
+  if (split)
+    conv_march_prep_split_kernel<<<ceil_div(32 * 2 * NT * 8, 256), 256, 0, st>>>(weight, reinterpret_cast<__half*>(wprep), Cout, Cin);
+  else
+    conv_march_prep_kernel<<<ceil_div(27 * 2 * NT * 8, 256), 256, 0, st>>>(weight, reinterpret_cast<__nv_bfloat16*>(wprep), Cout,
+                                                                         Cin);
   const unsigned grid = (unsigned)(tiles * DS);
   auto run = [&](auto kern) {
     cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e2 != cudaSuccess) {
-      set_error("conv3d(bf16 march): cannot reserve %d B of shared memory: %s", SMEM, cudaGetErrorString(e2));
+      set_error("%s: cannot reserve %d B of shared memory: %s", what, SMEM, cudaGetErrorString(e2));
       return SMILE_ERR_CUDA;
     }
     kern<<<grid, THREADS, SMEM, st>>>(in, wprep, bias, out, in_stats, out_stats, Cin, Cout, D, H, W, ntr, ntc, DS, act_out, eps);
-    return check_launch("conv3d(bf16 march)");
+    return check_launch(what);
   };
   int rc;
-  if (Cin <= 8)
-    rc = in_stats ? run(conv_march_kernel<true, true>) : run(conv_march_kernel<true, false>);
+  if (split)
+    rc = in_stats ? run(conv_march_kernel<true, true, true>) : run(conv_march_kernel<true, false, true>);
+  else if (Cin <= 8)
+    rc = in_stats ? run(conv_march_kernel<true, true, false>) : run(conv_march_kernel<true, false, false>);
   else
-    rc = in_stats ? run(conv_march_kernel<false, true>) : run(conv_march_kernel<false, false>);
+    rc = in_stats ? run(conv_march_kernel<false, true, false>) : run(conv_march_kernel<false, false, false>);
   cudaFreeAsync(wprep, st);
   return rc;
+}
+}  // namespace
+
+// Depth-marching bf16 tensor-core conv for Cin <= 16 and Cout <= 16.  *handled = false otherwise.
+int launch_conv3d_march_bf16(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
+                             double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
+                             cudaStream_t st, bool* handled) {
+  *handled = false;
+  if (Cin < 2 || Cin > 16 || Cout > 16 || D < 1 || H < 2 || W < 2) return SMILE_OK;
+  *handled = true;
+  return launch_march(false, in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st);
+}
+
+// Depth-marching fp16-split tensor-core conv (fp32-class accuracy) for 5..8 input and at most 8 output channels on
+// volumes wide enough to fill the 16 x 30 tiles.  SMILE_CONV_SPLIT=0 keeps those layers on the SIMT kernels, =2 takes
+// every shape that is legal (2 <= Cin <= 8, Cout <= 8).  *handled = false otherwise.
+int launch_conv3d_march_split(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
+                              double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
+                              cudaStream_t st, bool* handled) {
+  *handled = false;
+  static const int knob = [] { const char* e = getenv("SMILE_CONV_SPLIT"); return e ? atoi(e) : 1; }();
+  if (knob == 0) return SMILE_OK;
+  if (Cin < 2 || Cin > 8 || Cout > 8 || D < 1 || H < 2 || W < 2) return SMILE_OK;
+  if (knob != 2 && (Cin < 5 || W < 60 || H < 32 || D < 8)) return SMILE_OK;
+  *handled = true;
+  return launch_march(true, in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st);
 }
 
 }  // namespace smile

@@ -39,6 +39,9 @@ int launch_conv3d_bf16(const float* in, const float* weight, const float* bias, 
 int launch_conv3d_march_bf16(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
                              double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
                              cudaStream_t st, bool* handled);
+int launch_conv3d_march_split(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
+                             double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
+                             cudaStream_t st, bool* handled);
 long long conv3d_tc_prep_floats(int Cin, int Cout);
 int launch_conv3d_tc_prep(const float* weight, float* wprep, int Cin, int Cout, cudaStream_t st);
 int launch_conv3d_tma_flat(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,

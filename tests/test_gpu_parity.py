@@ -213,6 +213,49 @@ assert worst <= 1e-5, worst
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+def test_conv_fp16_split_tensor_core_path_forced():
+    """SMILE_CONV_SPLIT=2 sends every layer with 2..8 input and <= 8 output channels through the depth-marching fp16-split
+    tcgen05 kernel (by default only the 160-wide 8-channel layers use it): x = hi + 2^-11 lo operands, three products,
+    fp32-class accuracy.  Partial tiles in H and W, several depth splits, batch 2, normalise-on-load, LeakyReLU output,
+    large-magnitude inputs.  Same tolerance as the SIMT kernels.  The switch is read once per process: child process."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, torch
+sys.path.insert(0, '.')
+from oracle import modet_oracle as orc
+from smilecode_b200 import ops
+g = torch.Generator().manual_seed(22)
+worst = 0.0
+for cin, cout, shape, amp in [(8, 8, (5, 7, 80), 1.0), (6, 8, (4, 19, 33), 1.0), (8, 4, (9, 34, 64), 1.0), (2, 2, (6, 5, 26), 1.0),
+                              (5, 7, (12, 40, 31), 300.0), (8, 8, (3, 4, 10), 1e-3), (8, 8, (20, 48, 70), 1.0)]:
+    x = torch.randn(2, cin, *shape, generator=g) * amp
+    w1 = torch.randn(cin, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5
+    w2 = torch.randn(cout, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5
+    b1, b2 = torch.randn(cin, generator=g) * 0.1 * amp, torch.randn(cout, generator=g) * 0.1
+    r1 = orc.conv3(x, w1, b1)
+    ref = orc.conv3(orc.lrelu(orc.instance_norm(r1)), w2, b2)
+    raw, st = ops.conv3d(x.cuda(), w1.cuda(), b1.cuda(), want_stats=True)
+    e0 = float((raw.cpu() - r1).abs().max() / r1.abs().max())
+    out, st2 = ops.conv3d(raw, w2.cuda(), b2.cuda(), in_stats=st, want_stats=True)
+    act, _ = ops.conv3d(raw, w2.cuda(), b2.cuda(), in_stats=st, act_out=True)
+    e = float((out.cpu() - ref).abs().max() / ref.abs().max())
+    e = max(e, e0, float((act.cpu() - orc.lrelu(ref)).abs().max() / ref.abs().max()))
+    s = st2.cpu().reshape(2, cout, 2)
+    assert torch.allclose(s[..., 0], ref.double().sum(dim=(2, 3, 4)), rtol=1e-4, atol=1e-2), (cin, cout, shape)
+    assert torch.allclose(s[..., 1], (ref.double() ** 2).sum(dim=(2, 3, 4)), rtol=1e-4, atol=1e-2), (cin, cout, shape)
+    print(cin, cout, shape, 'relative error', e)
+    worst = max(worst, e)
+print('worst relative error', worst)
+assert worst <= 2e-6, worst
+"""
+    env = dict(os.environ, SMILE_CONV_SPLIT="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 def test_conv_prepared_weight_cache(ops):
     """Tensor-core conv with weights prepared once per nn.Parameter (inference): same result as the per-call path,
     and the cache follows in-place updates of the parameter."""

@@ -35,17 +35,29 @@ constexpr int SROWS = TR + 2;         // staged rows
 constexpr int PLANE_POS = 592;        // staged positions per plane (18 * 32 = 576, + the overhang of the last taps)
 constexpr int PLANE_BYTES = 2 * PLANE_POS * 16;   // two channel blocks of 8 bf16
 constexpr int RING = 4;
-constexpr int NT = 16;                // output channels (UMMA N)
-constexpr int B_BYTES = 32 * 2 * NT * 16;   // 27 taps (bf16, Cin > 8), 15 tap pairs (bf16, Cin <= 8), 2 x 15 + a zero block (fp16 split)
+constexpr int NT = 16;                // output channels per launch at most
 constexpr int WORKERS = 256;          // warps 0-7 stage the planes and drain the accumulators
 constexpr int THREADS = WORKERS + 32; // warp 8 only issues the MMAs (one lane): 108 per plane would otherwise delay warp 0
 constexpr int OFF_B = RING * PLANE_BYTES;
-// [0] weights landed, [1..2] MMAs of TMEM buffer 0 / 1 done, [3..4] plane staged (by step parity), [5..6] TMEM buffer drained
-constexpr int OFF_BAR = OFF_B + B_BYTES;
-constexpr int OFF_TMEM = OFF_BAR + 64;
-constexpr int OFF_MR = OFF_TMEM + 16;              // [16][2] rstd, -mean * rstd
-constexpr int OFF_RED = OFF_MR + 128 + 64;         // (+ 16 bias values); [8 warps][16][2] doubles
-constexpr int SMEM = OFF_RED + 8 * 16 * 2 * 8 + 16;
+// Precision / accumulator layout of a launch (template parameter SP):
+//   0  bf16 operands, one accumulator of 16 columns per M tile (configs[2..3] of BASELINE.json)
+//   1  fp16 split (fp32-class), Cout <= 8: MMA N = 16, two chains for the leading term, 32 columns per M tile
+//   2  fp16 split (fp32-class), Cout <= 16: MMA N = 32, one chain, 32 columns per M tile [ hh(16) | corr(16) ]
+template <int SP>
+struct Lay {
+  static constexpr int MMA_N = SP == 2 ? 32 : 16;
+  static constexpr int BLK = 2 * MMA_N * 16;                      // bytes of one B block (two K chunks of MMA_N rows)
+  static constexpr int NBLK = SP == 0 ? 27 : SP == 1 ? 32 : 30;   // SP 1: 2 x 15 + a zero block of N = 32 (two blocks)
+  static constexpr int B_BYTES = NBLK * BLK;
+  static constexpr int MCOLS = SP == 0 ? 16 : 32;                 // TMEM columns per M tile
+  static constexpr int TCOLS = 2 * MT * MCOLS;                    // two accumulator buffers
+  // [0] weights landed, [1..2] MMAs of TMEM buffer 0 / 1 done, [3..4] plane staged (by step parity), [5..6] buffer drained
+  static constexpr int OFF_BAR = OFF_B + B_BYTES;
+  static constexpr int OFF_TMEM = OFF_BAR + 64;
+  static constexpr int OFF_MR = OFF_TMEM + 16;              // [16][2] rstd, -mean * rstd
+  static constexpr int OFF_RED = OFF_MR + 128 + 64;         // (+ 16 bias values); [8 warps][16][2] doubles
+  static constexpr int SMEM = OFF_RED + 8 * 16 * 2 * 8 + 16;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -133,45 +145,57 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// weight [Cout <= 8][Cin <= 8][27] fp32 -> fp16 B operands [set 2][mma 15][cb 2][NT 16][8] + two all-zero blocks:
+// weight [Cout][CinT][27] fp32, input channels ci0 .. ci0 + Cin - 1 (Cin <= 8) -> fp16 B operands.
+// SP 1 (Cout <= 8):  [set 2][mma 15][cb 2][16 rows][8] + two all-zero blocks
 //   set 0, even pair: rows n < 8 = W_hi[n], rows n >= 8 = W_lo[n - 8];  odd pair: the two halves swapped
 //   set 1: rows n < 8 = 0, rows n >= 8 = W_hi[n - 8]
-__global__ void conv_march_prep_split_kernel(const float* __restrict__ w, __half* __restrict__ wprep, int Cout, int Cin) {
+// SP 2 (Cout <= 16): [set 2][mma 15][cb 2][32 rows][8]
+//   set 0: rows n < 16 = W_hi[n], rows n >= 16 = W_lo[n - 16];   set 1: rows n < 16 = 0, rows n >= 16 = W_hi[n - 16]
+template <int SP>
+__global__ void conv_march_prep_split_kernel(const float* __restrict__ w, __half* __restrict__ wprep, int Cout, int Cin,
+                                             int CinT, int ci0) {
+  constexpr int NR = Lay<SP>::MMA_N, NG = NR / 2;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= 32 * 2 * NT * 8) return;
-  if (e >= 30 * 2 * NT * 8) {
+  if (e >= Lay<SP>::B_BYTES / 2) return;
+  if (e >= 30 * 2 * NR * 8) {
     wprep[e] = __float2half_rn(0.f);
     return;
   }
   int t = e;
   const int j = t % 8; t /= 8;
-  const int n = t % NT; t /= NT;
+  const int n = t % NR; t /= NR;
   const int cb = t % 2; t /= 2;
   const int set = t / 15, i = t % 15;
   const int t0 = pair_first_tap(i);
   const bool single = (i % 5) == 4;
-  const int tap = t0 + cb, co = n & 7;
+  const int tap = t0 + cb, co = n % NG;
   float v = 0.f;
-  if (!(single && cb == 1) && j < Cin && co < Cout) v = w[((long long)co * Cin + j) * 27 + tap];
+  if (!(single && cb == 1) && j < Cin && co < Cout) v = w[((long long)co * CinT + ci0 + j) * 27 + tap];
   v = fminf(fmaxf(v, -65504.f), 65504.f);
   const __half h = __float2half_rn(v);
   const __half l = __float2half_rn((v - __half2float(h)) * 2048.f);
+  const bool swap = SP == 1 && (i & 1) != 0;
   __half r = __float2half_rn(0.f);
-  if (set == 0) r = ((n < 8) != ((i & 1) != 0)) ? h : l;
-  else if (n >= 8) r = h;
+  if (set == 0) r = ((n < NG) != swap) ? h : l;
+  else if (n >= NG) r = h;
   wprep[e] = r;
 }
 
 // CIN8: at most 8 input channels (the second channel block stays zero); NORM: InstanceNorm + LeakyReLU on load
-// SPLIT (with CIN8, Cout <= 8): fp16 hi / lo operands, see above; the second channel-block plane of a ring slot holds A_lo
-template <bool CIN8, bool NORM, bool SPLIT>
+// SP > 0 (with CIN8): fp16 hi / lo operands, see above; the second channel-block plane of a ring slot holds A_lo.
+// The input channels of this launch are ci0 .. ci0 + Cin - 1 of a tensor with CinT channels.  pass: 0 = the whole
+// reduction; 1 = first of two launches over the input channels (bias + partial sums stored raw, no statistics);
+// 2 = second (adds what pass 1 stored, then activation / statistics).
+template <bool CIN8, bool NORM, int SP>
 __global__ void __launch_bounds__(THREADS, 2)
 conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, const float* __restrict__ bias,
                   float* __restrict__ out, const double* __restrict__ in_stats, double* __restrict__ out_stats, int Cin,
-                  int Cout, int D, int H, int W, int ntr, int ntc, int DS, int act_out, float eps) {
+                  int Cout, int D, int H, int W, int ntr, int ntc, int DS, int act_out, float eps, int CinT, int ci0, int pass) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int MCOLS = SPLIT ? 32 : NT;        // TMEM columns per M tile
-  constexpr int TCOLS = 2 * MT * MCOLS;         // two accumulator buffers: 128 columns (bf16) or 256 (split)
+  using L = Lay<SP>;
+  constexpr bool SPLIT = SP != 0;
+  constexpr int MCOLS = L::MCOLS, TCOLS = L::TCOLS, MMA_N = L::MMA_N;
+  constexpr int OFF_BAR = L::OFF_BAR, OFF_TMEM = L::OFF_TMEM, OFF_MR = L::OFF_MR, OFF_RED = L::OFF_RED, B_BYTES = L::B_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
   float* s_mr = reinterpret_cast<float*>(smem + OFF_MR);
@@ -204,7 +228,7 @@ conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, 
   if (tid < 16) {
     float rstd = 1.f, shift = 0.f;
     if (NORM && tid < Cin) {
-      const double s = in_stats[((long long)b * Cin + tid) * 2], ss = in_stats[((long long)b * Cin + tid) * 2 + 1];
+      const double s = in_stats[((long long)b * CinT + ci0 + tid) * 2], ss = in_stats[((long long)b * CinT + ci0 + tid) * 2 + 1];
       const double mean = s / (double)N;
       const double var = fmax(ss / (double)N - mean * mean, 0.0);
       rstd = (float)(1.0 / sqrt(var + (double)eps));
@@ -221,7 +245,7 @@ conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  const float* inb = in + (long long)b * Cin * N;
+  const float* inb = in + ((long long)b * CinT + ci0) * N;
   constexpr int NCH = CIN8 ? 8 : 16;
   constexpr int PB = ((CIN8 && !SPLIT) ? 1 : 2) * PLANE_POS * 16;     // bytes of one staged plane (one or two blocks)
 
@@ -302,43 +326,58 @@ conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, 
     }
   };
 
+  // one accumulator column group of 8 -> registers
+  auto tld8 = [](uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+  };
   auto drain_plane = [&](int dd, int buf) {
 #pragma unroll
     for (int mm = 0; mm < 2; ++mm) {
       const int m = mbase + mm;
       const int h = h0 + 4 * m + q;
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * (MT * MCOLS) + m * MCOLS);
-      uint32_t r[16];
-      uint32_t r2[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-      if (SPLIT)
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                     : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7])
-                     : "r"(taddr + 16u));
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (col_ok && h < H) {
-        float* ob = out + (long long)b * Cout * N + (long long)dd * HW + h * W + (w0 + lane);
+      const bool live = col_ok && h < H;
+      float* ob = out + (long long)b * Cout * N + (long long)dd * HW + h * W + (w0 + lane);
+      // channel groups of 8: SP 0 columns [0-7 | 8-15]; SP 1 one group, columns hh_a 0-7, corr 8-15, hh_b 16-23;
+      // SP 2 two groups, columns hh 0-15, corr 16-31
 #pragma unroll
-        for (int n = 0; n < NT; ++n) {
-          if (n < Cout && (!SPLIT || n < 8)) {
-            const float val = (SPLIT ? fmaf(__uint_as_float(r[(n + 8) & 15]), 1.f / 2048.f,
-                                            __fadd_rn(__uint_as_float(r[n]), __uint_as_float(r2[n & 7])))
-                                     : __uint_as_float(r[n])) + s_bias[n];
-            ob[(long long)n * N] = act_out ? lrelu01(val) : val;
-            st_s[n] += val;
-            st_q[n] = fmaf(val, val, st_q[n]);
+      for (int g = 0; g < (SP == 1 ? 1 : 2); ++g) {
+        if (g * 8 >= Cout) break;
+        uint32_t r[8], rc[8], rb[8];
+        tld8(taddr + (uint32_t)(8 * g), r);
+        if (SP == 1) {
+          tld8(taddr + 8u, rc);
+          tld8(taddr + 16u, rb);
+        } else if (SP == 2) {
+          tld8(taddr + (uint32_t)(16 + 8 * g), rc);
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (live) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int n = 8 * g + i;
+            if (n < Cout) {
+              float val = __uint_as_float(r[i]);
+              if (SP == 1) val = fmaf(__uint_as_float(rc[i]), 1.f / 2048.f, __fadd_rn(val, __uint_as_float(rb[i])));
+              if (SP == 2) val = fmaf(__uint_as_float(rc[i]), 1.f / 2048.f, val);
+              if (pass == 2)
+                val += ob[(long long)n * N];      // partial sums (+ bias) of the first launch
+              else
+                val += s_bias[n];
+              ob[(long long)n * N] = (act_out && pass != 1) ? lrelu01(val) : val;
+              st_s[n] += val;
+              st_q[n] = fmaf(val, val, st_q[n]);
+            }
           }
         }
       }
     }
   };
 
-  // instruction descriptor: fp32 accumulate; A and B formats bf16 (1) or, in SPLIT mode, fp16 (0); N = 16, M = 128
-  const uint32_t idesc = (1u << 4) | (SPLIT ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // instruction descriptor: fp32 accumulate; A and B formats bf16 (1) or, in SPLIT mode, fp16 (0); N = MMA_N, M = 128
+  const uint32_t idesc = (1u << 4) | (SPLIT ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const uint32_t idesc32 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(32 >> 3) << 17);   // the same with N = 32
   const uint32_t ring_base = smem_u32(smem), b_base = smem_u32(smem + OFF_B);
 
@@ -390,7 +429,8 @@ conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, 
       uint32_t slot16[3];
 #pragma unroll
       for (int kd = 0; kd < 3; ++kd) slot16[kd] = (ring_base + (uint32_t)(((d - 1 + kd + RING) % RING) * PB)) >> 4;
-      const uint64_t db0 = make_desc(b_base, NT * 16, 128);
+      const uint64_t db0 = make_desc(b_base, MMA_N * 16, 128);
+      constexpr int BLK16 = 2 * MMA_N;        // one B block in 16-byte units
 #define SMILE_MMA(DCOL, DA, DB, FIRST)                                                                                     \
   if (FIRST)                                                                                                               \
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" \
@@ -410,16 +450,21 @@ conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, 
             // second tap t0 + 1: next column (distance 1 position) unless t0 ends a row (distance P - 2)
             const uint64_t hi = (kw == 2 && t0 != 8) ? da_wrap : da_row;   // the lone ninth tap: zero weights on chunk 2
             const uint64_t da = hi + (uint64_t)(slot16[kd] + (uint32_t)(m * 128 + kh * P + kw));
-            const uint64_t db = db0 + (uint64_t)(i * 2 * NT);
-            if (SPLIT) {
+            const uint64_t db = db0 + (uint64_t)(i * BLK16);
+            if (SP == 1) {
               if (i == 0) {   // clear the 32 columns of this M tile: any A x the zero block (N = 32), accumulate off
                 asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                             ::"r"(dcol), "l"(da), "l"(make_desc(b_base + 30 * 2 * NT * 16, 2 * NT * 16, 128)), "r"(idesc32) : "memory");
+                             ::"r"(dcol), "l"(da), "l"(make_desc(b_base + 30 * BLK16 * 16, 32 * 16, 128)), "r"(idesc32) : "memory");
               }
               // even pair: [W_hi | W_lo] -> hh_a, corr;  odd pair: [W_lo | W_hi] at column 8 -> corr, hh_b
               SMILE_MMA(dcol + ((i & 1) ? 8u : 0u), da, db, false)
               // A_lo (second block of the slot) x [0 | W_hi] (second set of B blocks) -> corr
-              SMILE_MMA(dcol, da + (uint64_t)PLANE_POS, db + (uint64_t)(15 * 2 * NT), false)
+              SMILE_MMA(dcol, da + (uint64_t)PLANE_POS, db + (uint64_t)(15 * BLK16), false)
+              continue;
+            }
+            if (SP == 2) {   // [W_hi | W_lo] -> hh, corr;  A_lo x [0 | W_hi] -> corr
+              SMILE_MMA(dcol, da, db, i == 0)
+              SMILE_MMA(dcol, da + (uint64_t)PLANE_POS, db + (uint64_t)(15 * BLK16), false)
               continue;
             }
             SMILE_MMA(dcol, da, db, i == 0)
@@ -430,7 +475,7 @@ conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, 
           for (int tap = 0; tap < 27; ++tap) {
             const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
             const uint64_t da = da_hi + (uint64_t)(slot16[kd] + (uint32_t)(m * 128 + kh * P + kw));
-            const uint64_t db = db0 + (uint64_t)(tap * 2 * NT);
+            const uint64_t db = db0 + (uint64_t)(tap * BLK16);
             SMILE_MMA(dcol, da, db, tap == 0)
           }
         }
@@ -445,7 +490,7 @@ conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TCOLS));
 
   // ---- InstanceNorm statistics: per-warp fp64 sums (flush_stats) -> one fp64 atomic per channel and CTA
-  if (out_stats != nullptr) {
+  if (out_stats != nullptr && pass != 1) {
     __syncthreads();
     if (tid < 2 * NT) {
       const int n = tid >> 1, which = tid & 1;
@@ -462,15 +507,18 @@ conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, 
 }  // namespace
 
 namespace {
-// common launch path of the two precisions
-int launch_march(bool split, const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
-                 double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps, cudaStream_t st) {
-  const char* what = split ? "conv3d(fp16-split march)" : "conv3d(bf16 march)";
+// common launch path: SP = 0 bf16, 1 / 2 fp16 split (Lay<SP>); input channels ci0 .. ci0 + Cin - 1 of CinT; pass as in the kernel
+template <int SP>
+int launch_march(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
+                 double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps, cudaStream_t st,
+                 int CinT, int ci0, int pass) {
+  using L = Lay<SP>;
+  const char* what = SP ? "conv3d(fp16-split march)" : "conv3d(bf16 march)";
   const int ntr = ceil_div(H, TR), ntc = ceil_div(W, TC);
   const long long tiles = (long long)B * ntr * ntc;
-  // Two CTAs per SM (92 KB of shared memory, 128 TMEM columns each): while one stages / drains, the other's MMAs run.
-  // The depth is split so that the grid is just under two full waves of 2 x 148 CTAs (measured: 288-576 CTAs beat 144
-  // and anything that leaves a partial third wave; each split re-stages two halo planes, which is not what bounds it).
+  // Two CTAs per SM (92-107 KB of shared memory, 128 / 256 TMEM columns each): while one stages / drains, the other's MMAs
+  // run.  The depth is split so that the grid is just under two full waves of 2 x 148 CTAs (measured: 288-576 CTAs beat
+  // 144 and anything that leaves a partial third wave; each split re-stages two halo planes, which is not what bounds it).
   static const int want = [] { const char* e = getenv("SMILE_MARCH_CTAS"); return e ? atoi(e) : 4 * kNumSMs; }();
   int DS = (int)(want / tiles);
   if (DS > D / 4) DS = D / 4;
@@ -487,33 +535,33 @@ int launch_march(bool split, const float* in, const float* weight, const float* 
     }
   });
   void* wprep = nullptr;
-  cudaError_t e = cudaMallocAsync(&wprep, B_BYTES, st);
+  cudaError_t e = cudaMallocAsync(&wprep, L::B_BYTES, st);
   if (e != cudaSuccess) {
     set_error("%s: cudaMallocAsync failed: %s", what, cudaGetErrorString(e));
     return SMILE_ERR_CUDA;
   }
-  if (split)
-    conv_march_prep_split_kernel<<<ceil_div(32 * 2 * NT * 8, 256), 256, 0, st>>>(weight, reinterpret_cast<__half*>(wprep), Cout, Cin);
+  if (SP)
+    conv_march_prep_split_kernel<SP><<<ceil_div(L::B_BYTES / 2, 256), 256, 0, st>>>(weight, reinterpret_cast<__half*>(wprep), Cout,
+                                                                                  Cin, CinT, ci0);
   else
     conv_march_prep_kernel<<<ceil_div(27 * 2 * NT * 8, 256), 256, 0, st>>>(weight, reinterpret_cast<__nv_bfloat16*>(wprep), Cout,
                                                                          Cin);
   const unsigned grid = (unsigned)(tiles * DS);
   auto run = [&](auto kern) {
-    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM);
     if (e2 != cudaSuccess) {
-      set_error("%s: cannot reserve %d B of shared memory: %s", what, SMEM, cudaGetErrorString(e2));
+      set_error("%s: cannot reserve %d B of shared memory: %s", what, L::SMEM, cudaGetErrorString(e2));
       return SMILE_ERR_CUDA;
     }
-    kern<<<grid, THREADS, SMEM, st>>>(in, wprep, bias, out, in_stats, out_stats, Cin, Cout, D, H, W, ntr, ntc, DS, act_out, eps);
+    kern<<<grid, THREADS, L::SMEM, st>>>(in, wprep, bias, out, in_stats, out_stats, Cin, Cout, D, H, W, ntr, ntc, DS, act_out, eps,
+                                         CinT, ci0, pass);
     return check_launch(what);
   };
   int rc;
-  if (split)
-    rc = in_stats ? run(conv_march_kernel<true, true, true>) : run(conv_march_kernel<true, false, true>);
-  else if (Cin <= 8)
-    rc = in_stats ? run(conv_march_kernel<true, true, false>) : run(conv_march_kernel<true, false, false>);
+  if (SP != 0 || Cin <= 8)
+    rc = in_stats ? run(conv_march_kernel<true, true, SP>) : run(conv_march_kernel<true, false, SP>);
   else
-    rc = in_stats ? run(conv_march_kernel<false, true, false>) : run(conv_march_kernel<false, false, false>);
+    rc = in_stats ? run(conv_march_kernel<false, true, 0>) : run(conv_march_kernel<false, false, 0>);
   cudaFreeAsync(wprep, st);
   return rc;
 }
@@ -526,22 +574,36 @@ int launch_conv3d_march_bf16(const float* in, const float* weight, const float* 
   *handled = false;
   if (Cin < 2 || Cin > 16 || Cout > 16 || D < 1 || H < 2 || W < 2) return SMILE_OK;
   *handled = true;
-  return launch_march(false, in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st);
+  return launch_march<0>(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st, Cin, 0, 0);
 }
 
-// Depth-marching fp16-split tensor-core conv (fp32-class accuracy) for 5..8 input and at most 8 output channels on
-// volumes wide enough to fill the 16 x 30 tiles.  SMILE_CONV_SPLIT=0 keeps those layers on the SIMT kernels, =2 takes
-// every shape that is legal (2 <= Cin <= 8, Cout <= 8).  *handled = false otherwise.
+// Depth-marching fp16-split tensor-core conv (fp32-class accuracy) for the wide levels: at most 16 output channels and
+// 2..16 input channels (more than 8 input channels = two launches over 8 + the rest, the second adds the first's partial
+// sums).  By default only where it beats the SIMT kernels (measured, tools/conv_compare.py): volumes that fill the
+// 16 x 30 tiles, 7..8 or 13..16 input channels (8->8 @160x192x160 755 -> 565 us, 8->16 @80x96x80 222 -> 113, 16->16 399 ->
+// 332; 4->8, 6->12, 12->12 are level or behind).  SMILE_CONV_SPLIT=0 keeps everything on the SIMT kernels, =2 takes every
+// legal shape.  *handled = false otherwise.
 int launch_conv3d_march_split(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
                               double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
                               cudaStream_t st, bool* handled) {
   *handled = false;
   static const int knob = [] { const char* e = getenv("SMILE_CONV_SPLIT"); return e ? atoi(e) : 1; }();
   if (knob == 0) return SMILE_OK;
-  if (Cin < 2 || Cin > 8 || Cout > 8 || D < 1 || H < 2 || W < 2) return SMILE_OK;
-  if (knob != 2 && (Cin < 5 || W < 60 || H < 32 || D < 8)) return SMILE_OK;
+  if (Cin < 2 || Cin > 16 || Cout > 16 || D < 1 || H < 2 || W < 2) return SMILE_OK;
+  if (knob != 2) {
+    if (W < 60 || H < 32 || D < 8) return SMILE_OK;
+    if (Cin < 7 || (Cin > 8 && (Cin < 13 || Cout < 12))) return SMILE_OK;
+  }
   *handled = true;
-  return launch_march(true, in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st);
+  auto go = [&](int cin, int ci0, int pass) {
+    if (Cout <= 8)
+      return launch_march<1>(in, weight, bias, out, in_stats, out_stats, B, cin, Cout, D, H, W, act_out, eps, st, Cin, ci0, pass);
+    return launch_march<2>(in, weight, bias, out, in_stats, out_stats, B, cin, Cout, D, H, W, act_out, eps, st, Cin, ci0, pass);
+  };
+  if (Cin <= 8) return go(Cin, 0, 0);
+  const int rc = go(8, 0, 1);
+  if (rc != SMILE_OK) return rc;
+  return go(Cin - 8, 8, 2);
 }
 
 }  // namespace smile

@@ -214,10 +214,11 @@ assert worst <= 1e-5, worst
 
 
 def test_conv_fp16_split_tensor_core_path_forced():
-    """SMILE_CONV_SPLIT=2 sends every layer with 2..8 input and <= 8 output channels through the depth-marching fp16-split
-    tcgen05 kernel (by default only the 160-wide 8-channel layers use it): x = hi + 2^-11 lo operands, three products,
-    fp32-class accuracy.  Partial tiles in H and W, several depth splits, batch 2, normalise-on-load, LeakyReLU output,
-    large-magnitude inputs.  Same tolerance as the SIMT kernels.  The switch is read once per process: child process."""
+    """SMILE_CONV_SPLIT=2 sends every layer with 2..16 input and <= 16 output channels through the depth-marching fp16-split
+    tcgen05 kernel (by default only the wide 8- / 16-channel layers use it): x = hi + 2^-11 lo operands, three products,
+    fp32-class accuracy; Cout <= 8 (two accumulation chains), Cout <= 16 (N = 32 MMAs), Cin > 8 (two launches).  Partial
+    tiles in H and W, several depth splits, batch 2, normalise-on-load, LeakyReLU output, large-magnitude inputs.  Same
+    tolerance as the SIMT kernels.  The switch is read once per process: child process."""
     import os
     import subprocess
     import sys
@@ -229,7 +230,9 @@ from smilecode_b200 import ops
 g = torch.Generator().manual_seed(22)
 worst = 0.0
 for cin, cout, shape, amp in [(8, 8, (5, 7, 80), 1.0), (6, 8, (4, 19, 33), 1.0), (8, 4, (9, 34, 64), 1.0), (2, 2, (6, 5, 26), 1.0),
-                              (5, 7, (12, 40, 31), 300.0), (8, 8, (3, 4, 10), 1e-3), (8, 8, (20, 48, 70), 1.0)]:
+                              (5, 7, (12, 40, 31), 300.0), (8, 8, (3, 4, 10), 1e-3), (8, 8, (20, 48, 70), 1.0),
+                              (8, 16, (6, 21, 64), 1.0), (6, 12, (9, 18, 35), 1.0), (16, 16, (10, 33, 62), 1.0),
+                              (12, 2, (5, 16, 40), 1.0), (13, 9, (8, 17, 30), 1.0)]:
     x = torch.randn(2, cin, *shape, generator=g) * amp
     w1 = torch.randn(cin, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5
     w2 = torch.randn(cout, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5

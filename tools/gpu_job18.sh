@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-( timeout 1500 python -m pytest tests/test_gpu_fullsize.py tests/test_gpu_parity.py -x -q -k "fullsize or full_size or end_to_end or lpba or mindboggle" 2>&1 | tail -8 )
+( timeout 1500 python -m pytest tests/test_gpu_fullsize.py -x -q -s 2>&1 | grep -E "ours|ref32|passed|failed" )
 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/job18_bench.json 2> gpurun_out/job18_bench.err
 python - <<'PY'
 import json

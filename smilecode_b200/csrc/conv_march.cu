@@ -135,9 +135,13 @@ __global__ void conv_march_prep_kernel(const float* __restrict__ w, __nv_bfloat1
 // MMA could be the "first" for all of its columns.
 // |x| must stay below the fp16 range (65504) after the normalise-on-load: operands are clamped there.
 // ---------------------------------------------------------------------------------------------------------------------
+// CLAMP: off for values that went through InstanceNorm (|z| <= sqrt(voxels) < 2^15 for any volume the kernel takes)
+template <bool CLAMP>
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  if (CLAMP) {
+    a = fminf(fmaxf(a, -65504.f), 65504.f);
+    b = fminf(fmaxf(b, -65504.f), 65504.f);
+  }
   const __half2 h = __floats2half2_rn(a, b);
   const float2 hf = __half22float2(h);
   const __half2 l = __floats2half2_rn((a - hf.x) * 2048.f, (b - hf.y) * 2048.f);
@@ -249,48 +253,76 @@ conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, 
   constexpr int NCH = CIN8 ? 8 : 16;
   constexpr int PB = ((CIN8 && !SPLIT) ? 1 : 2) * PLANE_POS * 16;     // bytes of one staged plane (one or two blocks)
 
-  // ---- stage one input plane (global depth dd) into its ring slot
+  // ---- stage one input plane (global depth dd) into its ring slot.  A thread stages the same (up to) three tile positions
+  // of every plane: their in-plane offsets and border predicates are computed once; element offsets are 32-bit (the
+  // launcher checks CinT * D * H * W < 2^31).  With at most 8 input channels the loads of all three positions are issued
+  // before the first is converted: one exposed memory latency per plane instead of three (long_scoreboard was the top
+  // stall of the workers, profiles/r04b_conv_split_full.txt).
+  int s_off[3];
+  bool s_ok[3];
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const int i = tid + it * WORKERS;
+    const int r = i >> 5, c = i & 31;
+    const int h = h0 - 1 + r, w = w0 - 1 + c;
+    s_ok[it] = i < SROWS * P && h >= 0 && h < H && w >= 0 && w < W;
+    s_off[it] = h * W + w;
+  }
+  const unsigned N32 = (unsigned)N;
+  auto convert_store = [&](uint4* slot, int i, float (&v)[NCH], bool ok) {
+    if (NORM) {
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const float x = fmaf(v[j], s_mr[2 * j], s_mr[2 * j + 1]);   // broadcast shared-memory reads
+        v[j] = (ok && j < Cin) ? fmaxf(x, 0.1f * x) : 0.f;
+      }
+    }
+    if (SPLIT) {
+      uint4 hi4, lo4;
+      split_pair<!NORM>(v[0], v[1], hi4.x, lo4.x);
+      split_pair<!NORM>(v[2], v[3], hi4.y, lo4.y);
+      split_pair<!NORM>(v[4], v[5], hi4.z, lo4.z);
+      split_pair<!NORM>(v[6], v[7], hi4.w, lo4.w);
+      slot[i] = hi4;
+      slot[PLANE_POS + i] = lo4;
+      return;
+    }
+    slot[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    if (!CIN8)
+      slot[PLANE_POS + i] =
+          make_uint4(pack_bf16(v[8 % NCH], v[9 % NCH]), pack_bf16(v[10 % NCH], v[11 % NCH]), pack_bf16(v[12 % NCH], v[13 % NCH]),
+                     pack_bf16(v[14 % NCH], v[15 % NCH]));
+  };
   auto stage_plane = [&](int dd) {
     uint4* slot = reinterpret_cast<uint4*>(smem + (size_t)((dd + RING) % RING) * PB);
     const bool plane_ok = dd >= 0 && dd < D;
+    const unsigned e0 = plane_ok ? (unsigned)(dd * HW) : 0u;
+    if (CIN8) {
+      float v[3][NCH];
 #pragma unroll
-    for (int it = 0; it < 3; ++it) {
-      const int i = tid + it * WORKERS;
-      if (i >= SROWS * P) break;
-      const int r = i >> 5, c = i & 31;
-      const int h = h0 - 1 + r, w = w0 - 1 + c;
-      float v[NCH];
-      const bool ok = plane_ok && h >= 0 && h < H && w >= 0 && w < W;
-      if (ok) {
-        const float* p = inb + (long long)dd * HW + h * W + w;
+      for (int it = 0; it < 3; ++it) {
+        const bool ok = plane_ok && s_ok[it];
+        const float* p = inb + (e0 + (unsigned)s_off[it]);
 #pragma unroll
-        for (int j = 0; j < NCH; ++j) v[j] = (j < Cin) ? __ldg(p + (long long)j * N) : 0.f;
-        if (NORM) {
-#pragma unroll
-          for (int j = 0; j < NCH; ++j) {
-            const float x = fmaf(v[j], s_mr[2 * j], s_mr[2 * j + 1]);   // broadcast shared-memory reads
-            v[j] = (j < Cin) ? fmaxf(x, 0.1f * x) : 0.f;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < NCH; ++j) v[j] = 0.f;
+        for (int j = 0; j < NCH; ++j) v[it][j] = (ok && j < Cin) ? __ldg(p + (unsigned)j * N32) : 0.f;
       }
-      if (SPLIT) {
-        uint4 hi4, lo4;
-        split_pair(v[0], v[1], hi4.x, lo4.x);
-        split_pair(v[2], v[3], hi4.y, lo4.y);
-        split_pair(v[4], v[5], hi4.z, lo4.z);
-        split_pair(v[6], v[7], hi4.w, lo4.w);
-        slot[i] = hi4;
-        slot[PLANE_POS + i] = lo4;
-        continue;
+#pragma unroll
+      for (int it = 0; it < 3; ++it) {
+        const int i = tid + it * WORKERS;
+        if (i < SROWS * P) convert_store(slot, i, v[it], plane_ok && s_ok[it]);
       }
-      slot[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-      if (!CIN8)
-        slot[PLANE_POS + i] =
-            make_uint4(pack_bf16(v[8 % NCH], v[9 % NCH]), pack_bf16(v[10 % NCH], v[11 % NCH]), pack_bf16(v[12 % NCH], v[13 % NCH]),
-                       pack_bf16(v[14 % NCH], v[15 % NCH]));
+    } else {
+#pragma unroll
+      for (int it = 0; it < 3; ++it) {
+        const int i = tid + it * WORKERS;
+        if (i >= SROWS * P) break;
+        const bool ok = plane_ok && s_ok[it];
+        float v[NCH];
+        const float* p = inb + (e0 + (unsigned)s_off[it]);
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) v[j] = (ok && j < Cin) ? __ldg(p + (unsigned)j * N32) : 0.f;
+        convert_store(slot, i, v, ok);
+      }
     }
   };
 
@@ -411,79 +443,92 @@ conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, 
       drain_plane(d1 - 1, pb);
       flush_stats();
     }
-  } else if (lane == 0) {
-    // ---------------- issuer: 4 x 27 MMAs per plane
-    mbar_wait(smem_u32(bars), 0);   // weights
-    uint32_t ph_s[2] = {0u, 0u}, ph_d[2] = {0u, 0u};
-    for (int d = d0; d < d1; ++d) {
-      const int par = (d - d0) & 1;
-      mbar_wait(smem_u32(bars + 3 + par), ph_s[par]);
-      ph_s[par] ^= 1u;
-      if (d - d0 >= 2) {            // the accumulator buffer was last used by plane d-2: drained?
-        mbar_wait(smem_u32(bars + 5 + par), ph_d[par]);
-        ph_d[par] ^= 1u;
-      }
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // Descriptors differ only in their 14-bit start-address field (16-byte units) -- and, for the paired taps of the
-      // Cin <= 8 variant, in the leading-dimension offset = distance between the two taps in the staged plane.
-      uint32_t slot16[3];
-#pragma unroll
-      for (int kd = 0; kd < 3; ++kd) slot16[kd] = (ring_base + (uint32_t)(((d - 1 + kd + RING) % RING) * PB)) >> 4;
-      const uint64_t db0 = make_desc(b_base, MMA_N * 16, 128);
-      constexpr int BLK16 = 2 * MMA_N;        // one B block in 16-byte units
-#define SMILE_MMA(DCOL, DA, DB, FIRST)                                                                                     \
+  } else {
+    // ---------------- issuer warp: one elected thread issues 4 x 27 (15, 30, 31) MMAs per plane.  The thread is chosen
+    // with elect.sync (the compiler then knows the region runs on ONE thread and feeds UTCHMMA from uniform registers
+    // without its generic per-lane ELECT / R2UR / branch loop), and a descriptor is a 32-bit add: only the 14-bit start
+    // address (and, for paired taps, the leading-dimension offset) in its LOW word changes; the high word (stride-dimension
+    // offset 128 B, descriptor version) is the constant 0x4008.
+    uint32_t leader = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    if (leader) {
+      mbar_wait(smem_u32(bars), 0);   // weights
+      uint32_t ph_s[2] = {0u, 0u}, ph_d[2] = {0u, 0u};
+      auto desc64 = [](uint32_t lo) {
+        uint64_t dsc;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(dsc) : "r"(lo), "r"(0x4008u));
+        return dsc;
+      };
+      constexpr uint32_t BLK16 = 2 * MMA_N;                                  // one B block in 16-byte units
+      const uint32_t db_lo = (b_base >> 4) | ((uint32_t)MMA_N << 16);        // LBO = MMA_N rows x 16 B between the K chunks
+      constexpr uint32_t LBO_ROW = 1u << 16, LBO_WRAP = (uint32_t)(P - 2) << 16, LBO_CB = (uint32_t)PLANE_POS << 16;
+#define SMILE_MMA(DCOL, DA, DB, IDESC, FIRST)                                                                              \
   if (FIRST)                                                                                                               \
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" \
-                 ::"r"(DCOL), "l"(DA), "l"(DB), "r"(idesc) : "memory");                                                    \
+                 ::"r"(DCOL), "l"(desc64(DA)), "l"(desc64(DB)), "r"(IDESC) : "memory");                                    \
   else                                                                                                                     \
     asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" \
-                 ::"r"(DCOL), "l"(DA), "l"(DB), "r"(idesc) : "memory");
+                 ::"r"(DCOL), "l"(desc64(DA)), "l"(desc64(DB)), "r"(IDESC) : "memory");
+      for (int d = d0; d < d1; ++d) {
+        const int par = (d - d0) & 1;
+        mbar_wait(smem_u32(bars + 3 + par), ph_s[par]);
+        ph_s[par] ^= 1u;
+        if (d - d0 >= 2) {            // the accumulator buffer was last used by plane d-2: drained?
+          mbar_wait(smem_u32(bars + 5 + par), ph_d[par]);
+          ph_d[par] ^= 1u;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t slot16[3];
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd) slot16[kd] = (ring_base + (uint32_t)(((d - 1 + kd + RING) % RING) * PB)) >> 4;
 #pragma unroll 1
-      for (int m = 0; m < MT; ++m) {
-        const uint32_t dcol = tmem + (uint32_t)(par * (MT * MCOLS) + m * MCOLS);
-        if (CIN8) {
-          const uint64_t da_row = make_desc(0u, 16, 128), da_wrap = make_desc(0u, (P - 2) * 16, 128);
+        for (int m = 0; m < MT; ++m) {
+          const uint32_t dcol = tmem + (uint32_t)(par * (MT * MCOLS) + m * MCOLS);
+          const uint32_t a0 = slot16[0] + (uint32_t)(m * 128), a1 = slot16[1] + (uint32_t)(m * 128),
+                         a2 = slot16[2] + (uint32_t)(m * 128);
+          if (CIN8) {
 #pragma unroll
-          for (int i = 0; i < 15; ++i) {
-            const int kd = i / 5, t0 = (i % 5) * 2;            // first tap of the pair inside the plane: 0 2 4 6 8
-            const int kh = t0 / 3, kw = t0 % 3;
-            // second tap t0 + 1: next column (distance 1 position) unless t0 ends a row (distance P - 2)
-            const uint64_t hi = (kw == 2 && t0 != 8) ? da_wrap : da_row;   // the lone ninth tap: zero weights on chunk 2
-            const uint64_t da = hi + (uint64_t)(slot16[kd] + (uint32_t)(m * 128 + kh * P + kw));
-            const uint64_t db = db0 + (uint64_t)(i * BLK16);
-            if (SP == 1) {
-              if (i == 0) {   // clear the 32 columns of this M tile: any A x the zero block (N = 32), accumulate off
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                             ::"r"(dcol), "l"(da), "l"(make_desc(b_base + 30 * BLK16 * 16, 32 * 16, 128)), "r"(idesc32) : "memory");
+            for (int i = 0; i < 15; ++i) {
+              const int kd = i / 5, t0 = (i % 5) * 2;            // first tap of the pair inside the plane: 0 2 4 6 8
+              const int kh = t0 / 3, kw = t0 % 3;
+              // second tap t0 + 1: next column (distance 1 position) unless t0 ends a row (distance P - 2); the lone ninth
+              // tap has zero weights on its second K chunk
+              const uint32_t lbo = (kw == 2 && t0 != 8) ? LBO_WRAP : LBO_ROW;
+              const uint32_t da = ((kd == 0) ? a0 : (kd == 1) ? a1 : a2) + (uint32_t)(kh * P + kw) + lbo;
+              const uint32_t db = db_lo + (uint32_t)i * BLK16;
+              if (SP == 1) {
+                if (i == 0) {   // clear the 32 columns of this M tile: any A x the zero block (N = 32), accumulate off
+                  SMILE_MMA(dcol, da, (b_base >> 4) + 30u * BLK16 + (32u << 16), idesc32, true)
+                }
+                // even pair: [W_hi | W_lo] -> hh_a, corr;  odd pair: [W_lo | W_hi] at column 8 -> corr, hh_b
+                SMILE_MMA(dcol + ((i & 1) ? 8u : 0u), da, db, idesc, false)
+                // A_lo (second block of the slot) x [0 | W_hi] (second set of B blocks) -> corr
+                SMILE_MMA(dcol, da + (uint32_t)PLANE_POS, db + 15u * BLK16, idesc, false)
+                continue;
               }
-              // even pair: [W_hi | W_lo] -> hh_a, corr;  odd pair: [W_lo | W_hi] at column 8 -> corr, hh_b
-              SMILE_MMA(dcol + ((i & 1) ? 8u : 0u), da, db, false)
-              // A_lo (second block of the slot) x [0 | W_hi] (second set of B blocks) -> corr
-              SMILE_MMA(dcol, da + (uint64_t)PLANE_POS, db + (uint64_t)(15 * BLK16), false)
-              continue;
+              if (SP == 2) {   // [W_hi | W_lo] -> hh, corr;  A_lo x [0 | W_hi] -> corr
+                SMILE_MMA(dcol, da, db, idesc, i == 0)
+                SMILE_MMA(dcol, da + (uint32_t)PLANE_POS, db + 15u * BLK16, idesc, false)
+                continue;
+              }
+              SMILE_MMA(dcol, da, db, idesc, i == 0)
             }
-            if (SP == 2) {   // [W_hi | W_lo] -> hh, corr;  A_lo x [0 | W_hi] -> corr
-              SMILE_MMA(dcol, da, db, i == 0)
-              SMILE_MMA(dcol, da + (uint64_t)PLANE_POS, db + (uint64_t)(15 * BLK16), false)
-              continue;
-            }
-            SMILE_MMA(dcol, da, db, i == 0)
-          }
-        } else {
-          const uint64_t da_hi = make_desc(0u, PLANE_POS * 16, 128);
+          } else {
 #pragma unroll
-          for (int tap = 0; tap < 27; ++tap) {
-            const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-            const uint64_t da = da_hi + (uint64_t)(slot16[kd] + (uint32_t)(m * 128 + kh * P + kw));
-            const uint64_t db = db0 + (uint64_t)(tap * BLK16);
-            SMILE_MMA(dcol, da, db, tap == 0)
+            for (int tap = 0; tap < 27; ++tap) {
+              const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+              const uint32_t da = ((kd == 0) ? a0 : (kd == 1) ? a1 : a2) + (uint32_t)(kh * P + kw) + LBO_CB;
+              const uint32_t db = db_lo + (uint32_t)tap * BLK16;
+              SMILE_MMA(dcol, da, db, idesc, tap == 0)
+            }
           }
         }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bars + 1 + par))
+                     : "memory");
       }
 #undef SMILE_MMA
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bars + 1 + par))
-                   : "memory");
     }
+    __syncwarp();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -573,6 +618,7 @@ int launch_conv3d_march_bf16(const float* in, const float* weight, const float* 
                              cudaStream_t st, bool* handled) {
   *handled = false;
   if (Cin < 2 || Cin > 16 || Cout > 16 || D < 1 || H < 2 || W < 2) return SMILE_OK;
+  if ((long long)Cin * D * H * W >= (1LL << 31)) return SMILE_OK;   // 32-bit element offsets inside the kernel
   *handled = true;
   return launch_march<0>(in, weight, bias, out, in_stats, out_stats, B, Cin, Cout, D, H, W, act_out, eps, st, Cin, 0, 0);
 }
@@ -590,6 +636,7 @@ int launch_conv3d_march_split(const float* in, const float* weight, const float*
   static const int knob = [] { const char* e = getenv("SMILE_CONV_SPLIT"); return e ? atoi(e) : 1; }();
   if (knob == 0) return SMILE_OK;
   if (Cin < 2 || Cin > 16 || Cout > 16 || D < 1 || H < 2 || W < 2) return SMILE_OK;
+  if ((long long)Cin * D * H * W >= (1LL << 30)) return SMILE_OK;   // 32-bit element offsets; |z| after InstanceNorm < 2^15
   if (knob != 2) {
     if (W < 60 || H < 32 || D < 8) return SMILE_OK;
     if (Cin < 7 || (Cin > 8 && (Cin < 13 || Cout < 12))) return SMILE_OK;

@@ -99,6 +99,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 //             plane (A's second K chunk is the same staged plane shifted by the tap distance, see the issuer), the ninth
 //             tap of a plane goes alone with a zero second block: 15 MMAs per M tile instead of 27.
 __device__ __forceinline__ int pair_first_tap(int i) { return (i / 5) * 9 + (i % 5) * 2; }   // mma i of 15 -> its first tap
+//   Cin <= 4: [mma 9][cb 2][NT][8]: MMA i = kernel row (kd, kh); block 0 holds taps kw = 0 (j < 4) and kw = 1 (j >= 4), block 1
+//             tap kw = 2 (j < 4) and zeros.
+__device__ __forceinline__ int row_tap(int i, int cb, int j) { return (j >= 4 && cb == 1) ? -1 : i * 3 + 2 * cb + (j >> 2); }
 __global__ void conv_march_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wprep, int Cout, int Cin) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= 27 * 2 * NT * 8) return;
@@ -107,7 +110,10 @@ __global__ void conv_march_prep_kernel(const float* __restrict__ w, __nv_bfloat1
   const int n = t % NT; t /= NT;
   const int cb = t % 2; t /= 2;
   float v = 0.f;
-  if (Cin > 8) {
+  if (Cin <= 4) {
+    const int tap = t < 9 ? row_tap(t, cb, j) : -1;
+    if (tap >= 0 && (j & 3) < Cin && n < Cout) v = w[((long long)n * Cin + (j & 3)) * 27 + tap];
+  } else if (Cin > 8) {
     const int tap = t, ci = cb * 8 + j;
     if (ci < Cin && n < Cout) v = w[((long long)n * Cin + ci) * 27 + tap];
   } else if (t < 15) {
@@ -170,11 +176,17 @@ __global__ void conv_march_prep_split_kernel(const float* __restrict__ w, __half
   const int n = t % NR; t /= NR;
   const int cb = t % 2; t /= 2;
   const int set = t / 15, i = t % 15;
-  const int t0 = pair_first_tap(i);
-  const bool single = (i % 5) == 4;
-  const int tap = t0 + cb, co = n % NG;
+  const int co = n % NG;
   float v = 0.f;
-  if (!(single && cb == 1) && j < Cin && co < Cout) v = w[((long long)co * CinT + ci0 + j) * 27 + tap];
+  if (Cin <= 4) {      // kernel rows: see conv_march_prep_kernel
+    const int tap = i < 9 ? row_tap(i, cb, j) : -1;
+    if (tap >= 0 && (j & 3) < Cin && co < Cout) v = w[((long long)co * CinT + ci0 + (j & 3)) * 27 + tap];
+  } else {
+    const int t0 = pair_first_tap(i);
+    const bool single = (i % 5) == 4;
+    const int tap = t0 + cb;
+    if (!(single && cb == 1) && j < Cin && co < Cout) v = w[((long long)co * CinT + ci0 + j) * 27 + tap];
+  }
   v = fminf(fmaxf(v, -65504.f), 65504.f);
   const __half h = __float2half_rn(v);
   const __half l = __float2half_rn((v - __half2float(h)) * 2048.f);
@@ -190,7 +202,10 @@ __global__ void conv_march_prep_split_kernel(const float* __restrict__ w, __half
 // The input channels of this launch are ci0 .. ci0 + Cin - 1 of a tensor with CinT channels.  pass: 0 = the whole
 // reduction; 1 = first of two launches over the input channels (bias + partial sums stored raw, no statistics);
 // 2 = second (adds what pass 1 stored, then activation / statistics).
-template <bool CIN8, bool NORM, int SP>
+// CIN4 (with CIN8): at most 4 input channels.  A staged position holds its own 4 channels and those of its right-hand
+// neighbour, so a 16-byte K chunk is TWO taps (kw, kw+1) and a K = 16 MMA covers a whole kernel row (kw = 0, 1 | 2, -):
+// 9 MMAs per M tile and operand set instead of 15.
+template <bool CIN8, bool NORM, int SP, bool CIN4>
 __global__ void __launch_bounds__(THREADS, 2)
 conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, const float* __restrict__ bias,
                   float* __restrict__ out, const double* __restrict__ in_stats, double* __restrict__ out_stats, int Cin,
@@ -277,6 +292,13 @@ conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, 
         v[j] = (ok && j < Cin) ? fmaxf(x, 0.1f * x) : 0.f;
       }
     }
+    if (CIN4) {   // channels 4-7 of a position = channels 0-3 of its right-hand neighbour (lanes run along the row)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float nb = __shfl_down_sync(0xffffffffu, v[j], 1);
+        v[4 + j] = (lane < 31) ? nb : 0.f;
+      }
+    }
     if (SPLIT) {
       uint4 hi4, lo4;
       split_pair<!NORM>(v[0], v[1], hi4.x, lo4.x);
@@ -304,7 +326,7 @@ conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, 
         const bool ok = plane_ok && s_ok[it];
         const float* p = inb + (e0 + (unsigned)s_off[it]);
 #pragma unroll
-        for (int j = 0; j < NCH; ++j) v[it][j] = (ok && j < Cin) ? __ldg(p + (unsigned)j * N32) : 0.f;
+        for (int j = 0; j < NCH; ++j) v[it][j] = (ok && j < Cin && !(CIN4 && j >= 4)) ? __ldg(p + (unsigned)j * N32) : 0.f;
       }
 #pragma unroll
       for (int it = 0; it < 3; ++it) {
@@ -489,11 +511,14 @@ conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, 
           if (CIN8) {
 #pragma unroll
             for (int i = 0; i < 15; ++i) {
-              const int kd = i / 5, t0 = (i % 5) * 2;            // first tap of the pair inside the plane: 0 2 4 6 8
+              if (CIN4 && i >= 9) break;
+              // CIN4: MMA i = kernel row (kd, kh): K chunk 0 = taps kw 0, 1 at the row's first position, chunk 1 = taps
+              // kw 2, - two positions further.  Otherwise MMA i = tap pair:
+              const int kd = CIN4 ? i / 3 : i / 5, t0 = CIN4 ? (i % 3) * 3 : (i % 5) * 2;   // first tap inside the plane
               const int kh = t0 / 3, kw = t0 % 3;
               // second tap t0 + 1: next column (distance 1 position) unless t0 ends a row (distance P - 2); the lone ninth
               // tap has zero weights on its second K chunk
-              const uint32_t lbo = (kw == 2 && t0 != 8) ? LBO_WRAP : LBO_ROW;
+              const uint32_t lbo = CIN4 ? (2u << 16) : (kw == 2 && t0 != 8) ? LBO_WRAP : LBO_ROW;
               const uint32_t da = ((kd == 0) ? a0 : (kd == 1) ? a1 : a2) + (uint32_t)(kh * P + kw) + lbo;
               const uint32_t db = db_lo + (uint32_t)i * BLK16;
               if (SP == 1) {
@@ -603,10 +628,12 @@ int launch_march(const float* in, const float* weight, const float* bias, float*
     return check_launch(what);
   };
   int rc;
-  if (SP != 0 || Cin <= 8)
-    rc = in_stats ? run(conv_march_kernel<true, true, SP>) : run(conv_march_kernel<true, false, SP>);
+  if (Cin <= 4)
+    rc = in_stats ? run(conv_march_kernel<true, true, SP, true>) : run(conv_march_kernel<true, false, SP, true>);
+  else if (SP != 0 || Cin <= 8)
+    rc = in_stats ? run(conv_march_kernel<true, true, SP, false>) : run(conv_march_kernel<true, false, SP, false>);
   else
-    rc = in_stats ? run(conv_march_kernel<false, true, 0>) : run(conv_march_kernel<false, false, 0>);
+    rc = in_stats ? run(conv_march_kernel<false, true, 0, false>) : run(conv_march_kernel<false, false, 0, false>);
   cudaFreeAsync(wprep, st);
   return rc;
 }
@@ -626,8 +653,10 @@ int launch_conv3d_march_bf16(const float* in, const float* weight, const float* 
 // Depth-marching fp16-split tensor-core conv (fp32-class accuracy) for the wide levels: at most 16 output channels and
 // 2..16 input channels (more than 8 input channels = two launches over 8 + the rest, the second adds the first's partial
 // sums).  By default only where it beats the SIMT kernels (measured, tools/conv_compare.py): volumes that fill the
-// 16 x 30 tiles, 7..8 or 13..16 input channels (8->8 @160x192x160 755 -> 565 us, 8->16 @80x96x80 222 -> 113, 16->16 399 ->
-// 332; 4->8, 6->12, 12->12 are level or behind).  SMILE_CONV_SPLIT=0 keeps everything on the SIMT kernels, =2 takes every
+// 16 x 30 tiles, 4, 6..8 or 13..16 input channels and enough output channels (the cost does not shrink with Cin below 8
+// -- except for Cin <= 4, which packs a whole kernel row into one MMA -- nor with Cout; the SIMT kernels' does):
+// 4->8 @160x192x160 432 -> 338 us, 8->8 755 -> 498, 8->16 @80x96x80 222 -> 103, 16->16 399 -> 318, 6->12 87 -> 78; 12->12 is
+// behind (170 vs 148).  SMILE_CONV_SPLIT=0 keeps everything on the SIMT kernels, =2 takes every
 // legal shape.  *handled = false otherwise.
 int launch_conv3d_march_split(const float* in, const float* weight, const float* bias, float* out, const double* in_stats,
                               double* out_stats, int B, int Cin, int Cout, int D, int H, int W, int act_out, float eps,
@@ -639,7 +668,7 @@ int launch_conv3d_march_split(const float* in, const float* weight, const float*
   if ((long long)Cin * D * H * W >= (1LL << 30)) return SMILE_OK;   // 32-bit element offsets; |z| after InstanceNorm < 2^15
   if (knob != 2) {
     if (W < 60 || H < 32 || D < 8) return SMILE_OK;
-    if (Cin < 7 || (Cin > 8 && (Cin < 13 || Cout < 12))) return SMILE_OK;
+    if (Cin <= 8 ? !((Cin == 4 || Cin >= 6) && Cout >= 6) : !(Cin >= 13 && Cout >= 8)) return SMILE_OK;
   }
   *handled = true;
   auto go = [&](int cin, int ci0, int pass) {

@@ -232,7 +232,8 @@ worst = 0.0
 for cin, cout, shape, amp in [(8, 8, (5, 7, 80), 1.0), (6, 8, (4, 19, 33), 1.0), (8, 4, (9, 34, 64), 1.0), (2, 2, (6, 5, 26), 1.0),
                               (5, 7, (12, 40, 31), 300.0), (8, 8, (3, 4, 10), 1e-3), (8, 8, (20, 48, 70), 1.0),
                               (8, 16, (6, 21, 64), 1.0), (6, 12, (9, 18, 35), 1.0), (16, 16, (10, 33, 62), 1.0),
-                              (12, 2, (5, 16, 40), 1.0), (13, 9, (8, 17, 30), 1.0)]:
+                              (12, 2, (5, 16, 40), 1.0), (13, 9, (8, 17, 30), 1.0), (4, 8, (7, 20, 66), 1.0),
+                              (3, 5, (4, 9, 31), 1.0)]:
     x = torch.randn(2, cin, *shape, generator=g) * amp
     w1 = torch.randn(cin, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5
     w2 = torch.randn(cout, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5

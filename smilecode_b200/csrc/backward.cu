@@ -6,6 +6,8 @@
 //   cwm_fuse_bwd      softmax-weighted field fusion backward                          (models.py:268-275)
 // All are HBM/L2-bound streaming or gather/scatter kernels: one thread per voxel, lanes along W,
 // parameter gradients reduced warp -> CTA -> one atomicAdd per CTA and element.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -475,6 +477,84 @@ __global__ void __launch_bounds__(256) cwm_fuse_bwd_kernel(const float* __restri
   }
 }
 
+// The same with warp-aggregated scatter (volumes below 2^31 voxels).  Lanes run along W, and with a smooth flow the x1
+// corner of lane L is the x0 corner of lane L+1 in the same (z, y) row: lane L adds its neighbour's x0 contribution to
+// its own x1 contribution and issues ONE atomic for the pair, the neighbour skips its x0 atomic.  Equality of the linear
+// indices is all that is tested, so row ends, clamped corners and rough flows just fall back to separate atomics.  Half
+// the atomics of the kernel above where it matters (64 per voxel at 8 channels: 1.3 ms at 160x192x160).
+__global__ void __launch_bounds__(256) warp3d_bwd_agg_kernel(const float* __restrict__ g, const float* __restrict__ src,
+                                                             const float* __restrict__ flow, float* __restrict__ d_src,
+                                                             float* __restrict__ d_flow, int C, int D, int H, int W) {
+  const int HW = H * W;
+  const int N = D * HW;
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const float* fl = flow + (long long)b * 3 * N;
+  const float* sb = src + (long long)b * C * N;
+  const float* gb = g + (long long)b * C * N;
+  const float dm1 = (float)(D - 1), hm1 = (float)(H - 1), wm1 = (float)(W - 1);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < N; base += stride) {
+    const bool valid = base + lane < N;
+    const int p = valid ? (int)(base + lane) : N - 1;
+    const int d = p / HW;
+    const int r = p - d * HW;
+    const int h = r / W, w = r - h * W;
+    const Axis az = axis_of(st_coord(d, __ldg(fl + p), dm1), D);
+    const Axis ay = axis_of(st_coord(h, __ldg(fl + N + p), hm1), H);
+    const Axis ax = axis_of(st_coord(w, __ldg(fl + 2 * N + p), wm1), W);
+    const int zi[2] = {az.i0, az.i1}, yi[2] = {ay.i0, ay.i1};
+    const float wz[2] = {az.w0, az.w1}, wy[2] = {ay.w0, ay.w1}, wx[2] = {ax.w0, ax.w1};
+    const float mz[2] = {az.m0, az.m1}, my[2] = {ay.m0, ay.m1}, mx[2] = {ax.m0, ax.m1};
+    // which of this lane's four (z, y) rows continue into the next lane's row, and which are continued by the previous
+    bool merge[4], absorbed[4];
+    int o0[4], o1[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int row = (zi[q >> 1] * H + yi[q & 1]) * W;
+      o0[q] = row + ax.i0;
+      o1[q] = row + ax.i1;
+      const int o0n = __shfl_down_sync(0xffffffffu, o0[q], 1), o1p = __shfl_up_sync(0xffffffffu, o1[q], 1);
+      merge[q] = lane < 31 && o0n == o1[q];
+      absorbed[q] = lane > 0 && o1p == o0[q];
+    }
+    float gz = 0.f, gy = 0.f, gx = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float gv = valid ? __ldg(gb + (long long)c * N + p) : 0.f;
+      const float* sc = sb + (long long)c * N;
+      float* dc = d_src ? d_src + ((long long)b * C + c) * N : nullptr;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int cz = q >> 1, cy = q & 1;
+        if (dc != nullptr) {     // uniform
+          const float a = (wx[0] * wy[cy] * wz[cz]) * gv;
+          float bb = (wx[1] * wy[cy] * wz[cz]) * gv;
+          const float an = __shfl_down_sync(0xffffffffu, a, 1);
+          if (merge[q]) bb += an;
+          if (bb != 0.f) atomicAdd(dc + o1[q], bb);
+          if (!absorbed[q] && a != 0.f) atomicAdd(dc + o0[q], a);
+        }
+        if (d_flow != nullptr) {
+          const float v0 = __ldg(sc + o0[q]) * gv, v1 = __ldg(sc + o1[q]) * gv;
+          const float sy = cy ? my[1] : -my[0], sz = cz ? mz[1] : -mz[0];
+          gx = fmaf(v0 * -mx[0], wy[cy] * wz[cz], gx);
+          gy = fmaf(v0 * sy, wx[0] * wz[cz], gy);
+          gz = fmaf(v0 * sz, wx[0] * wy[cy], gz);
+          gx = fmaf(v1 * mx[1], wy[cy] * wz[cz], gx);
+          gy = fmaf(v1 * sy, wx[1] * wz[cz], gy);
+          gz = fmaf(v1 * sz, wx[1] * wy[cy], gz);
+        }
+      }
+    }
+    if (d_flow != nullptr && valid) {
+      float* df = d_flow + (long long)b * 3 * N;
+      df[p] = gz;
+      df[N + p] = gy;
+      df[2 * N + p] = gx;
+    }
+  }
+}
+
 }  // namespace
 
 int launch_warp3d_bwd(const float* g, const float* src, const float* flow, float* d_src, float* d_flow, int B, int C, int D,
@@ -487,7 +567,11 @@ int launch_warp3d_bwd(const float* g, const float* src, const float* flow, float
       return SMILE_ERR_CUDA;
     }
   }
-  warp3d_bwd_kernel<<<dim3(grid_for(N, 256, 32), B), 256, 0, st>>>(g, src, flow, d_src, d_flow, C, D, H, W);
+  static const bool no_agg = getenv("SMILE_WARP_BWD_PLAIN") != nullptr;   // A/B knob
+  if (N < (1LL << 31) && !no_agg)
+    warp3d_bwd_agg_kernel<<<dim3(grid_for(N, 256, 32), B), 256, 0, st>>>(g, src, flow, d_src, d_flow, C, D, H, W);
+  else
+    warp3d_bwd_kernel<<<dim3(grid_for(N, 256, 32), B), 256, 0, st>>>(g, src, flow, d_src, d_flow, C, D, H, W);
   return check_launch("warp3d_bwd");
 }
 

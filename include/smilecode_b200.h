@@ -195,6 +195,11 @@ int smile_cwm_fuse_bwd(const float* g, const float* fields, const float* logits,
 int smile_conv3d_flip_weights(const float* w, float* wT, int Cout, int Cin, smile_stream_t stream);
 int smile_conv3d_wgrad(const float* in, const float* d_out, float* d_w, float* d_b, int B, int Cin, int Cout, int D, int H,
                        int W, smile_stream_t stream);
+/* The same weight / bias gradient with the products on bf16 tensor cores (tcgen05, fp32 accumulation; operands rounded to
+ * bf16: ~3e-3 relative on a gradient element) -- the weight-gradient half of the bf16 training mode, next to
+ * smile_conv3d_bf16_fwd for the forward and data-gradient products. */
+int smile_conv3d_wgrad_bf16(const float* in, const float* d_out, float* d_w, float* d_b, int B, int Cin, int Cout, int D,
+                            int H, int W, smile_stream_t stream);
 
 /* InstanceNorm3d + LeakyReLU(0.1) backward (models.py:148-150): act = lrelu(IN(raw)); given d_act, act and the forward
  * fp64 (sum, sumsq) of raw, writes d_raw.  mode 0: IN + LeakyReLU; mode 1: LeakyReLU only (ConvBlock, models.py:131-132;

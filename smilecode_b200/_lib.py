@@ -36,6 +36,7 @@ SIGNATURES = {
     "smile_cwm_fuse_bwd": [P, P, P, P, P, c_int, c_int, c_longlong, P],
     "smile_conv3d_flip_weights": [P, P, c_int, c_int, P],
     "smile_conv3d_wgrad": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "smile_conv3d_wgrad_bf16": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "smile_in_lrelu_bwd": [P, P, P, P, P, c_int, c_int, c_longlong, c_float, c_int, P],
     "smile_avgpool2_bwd_add": [P, P, c_int, c_int, c_int, c_int, c_int, P],
     "smile_ncc_vxm_bwd": [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],

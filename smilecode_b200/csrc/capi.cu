@@ -3,8 +3,8 @@
 #include <cstdio>
 
 #include "../../include/smilecode_b200.h"
-#include "common.cuh"
 #include <cstdlib>
+#include "common.cuh"
 
 #include "kernels.h"
 
@@ -364,6 +364,31 @@ int smile_conv3d_wgrad(const float* in, const float* d_out, float* d_w, float* d
   REQUIRE_VOL(B, D, H, W);
   REQUIRE(Cin > 0 && Cout > 0 && B <= 65535, "%s: bad sizes", __func__);
   return launch_conv3d_wgrad(in, d_out, d_w, d_b, B, Cin, Cout, D, H, W, (cudaStream_t)stream);
+}
+
+int smile_conv3d_wgrad_bf16(const float* in, const float* d_out, float* d_w, float* d_b, int B, int Cin, int Cout, int D,
+                            int H, int W, smile_stream_t stream) {
+  REQUIRE_PTR(in);
+  REQUIRE_PTR(d_out);
+  REQUIRE_PTR(d_w);
+  REQUIRE_VOL(B, D, H, W);
+  REQUIRE(Cin > 0 && Cout > 0 && Cin <= 4096 && Cout <= 4096, "%s: Cin=%d Cout=%d out of range", __func__, Cin, Cout);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(d_w, 0, (size_t)Cout * Cin * 27 * sizeof(float), st) != cudaSuccess ||
+      (d_b != nullptr && cudaMemsetAsync(d_b, 0, (size_t)Cout * sizeof(float), st) != cudaSuccess)) {
+    set_error("%s: memset failed", __func__);
+    return SMILE_ERR_CUDA;
+  }
+  // The im2col build of the tensor-core kernel reads the activations with scattered 4-byte loads (L1-bound): it wins from the
+  // 80-wide level down (16->16 @80x96x80 0.71 -> 0.47 ms, 128->128 @10x12x10 0.51 -> < 0.1) and loses on the 160-wide level
+  // (8->8 1.10 -> 1.60), which stays on the SIMT kernels.  SMILE_WGRAD_TC=2 forces it everywhere, =0 switches it off.
+  static const int knob = [] { const char* e = getenv("SMILE_WGRAD_TC"); return e ? atoi(e) : 1; }();
+  if (knob == 2 || (knob == 1 && (long long)D * H * W <= 80LL * 96 * 80)) {
+    bool handled = false;
+    const int rc = launch_conv3d_wgrad_tc(in, d_out, d_w, d_b, B, Cin, Cout, D, H, W, st, &handled);
+    if (handled) return rc;
+  }
+  return launch_conv3d_wgrad(in, d_out, d_w, d_b, B, Cin, Cout, D, H, W, st);
 }
 
 int smile_in_lrelu_bwd(const float* d_act, const float* act, const double* fwd_stats, void* work, float* d_raw, int B, int C,

@@ -89,6 +89,8 @@ int launch_cwm_fuse_bwd(const float* g, const float* fields, const float* logits
 int launch_conv3d_flip_weights(const float* w, float* wT, int Cout, int Cin, cudaStream_t st);
 int launch_conv3d_wgrad(const float* x, const float* dy, float* dw, float* db, int B, int Cin, int Cout, int D, int H,
                         int W, cudaStream_t st);
+int launch_conv3d_wgrad_tc(const float* x, const float* dy, float* dw, float* db, int B, int Cin, int Cout, int D, int H,
+                           int W, cudaStream_t st, bool* handled);
 int launch_in_lrelu_bwd(const float* da, const float* act, const double* fwd_stats, double* sums_work, float* dy, int B,
                         int C, long long N, float eps, int mode, cudaStream_t st);
 int launch_pool_bwd_add(const float* dpooled, float* dfull, int B, int C, int D, int H, int W, cudaStream_t st);

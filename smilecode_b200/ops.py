@@ -481,7 +481,9 @@ def conv3d_bwd(g: Tensor, x: Tensor, weight: Tensor, need_x: bool = True, need_b
         dx, _ = conv3d(g, wT, zero_b)
     dw = torch.empty_like(weight)
     db = torch.empty(Cout, device=x.device, dtype=torch.float32) if need_bias else None
-    call("smile_conv3d_wgrad", x.data_ptr(), g.data_ptr(), dw.data_ptr(), _ptr(db), B, Cin, Cout, D, H, W, _stream(),
+    # bf16 mode: the weight-gradient products also run on the tensor cores (wgrad_tc.cu)
+    entry = "smile_conv3d_wgrad_bf16" if _CONV_PRECISION == "bf16" else "smile_conv3d_wgrad"
+    call(entry, x.data_ptr(), g.data_ptr(), dw.data_ptr(), _ptr(db), B, Cin, Cout, D, H, W, _stream(),
          label=f"[{Cin}->{Cout} {D}x{H}x{W}]")
     return dx, dw, db
 

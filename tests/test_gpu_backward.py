@@ -146,6 +146,35 @@ def test_conv_lrelu_and_plain_conv_backward():
         assert rel(bd.grad.cpu(), br.grad) <= 2e-5
 
 
+@pytest.mark.parametrize("cin,cout,shape,batch", [(8, 8, (6, 12, 40), 2), (4, 8, (5, 7, 16), 1), (6, 12, (4, 9, 20), 2),
+                                                  (16, 16, (3, 6, 10), 2), (32, 64, (5, 6, 10), 2), (128, 128, (2, 3, 5), 2),
+                                                  (3, 5, (4, 5, 7), 3), (20, 70, (3, 4, 6), 1)])
+def test_conv_weight_gradient_on_tensor_cores(cin, cout, shape, batch):
+    """smile_conv3d_wgrad_bf16 (tcgen05, im2col built in shared memory, K = positions): against the fp32 weight gradient of
+    the SAME bf16-rounded operands (tight: only the accumulation order differs) and against the fp32 gradient of the
+    original operands (bf16 rounding: ~3e-3 relative).  Row-crossing position groups (W not a multiple of 8), partial
+    channel tiles, several output-channel tiles, batch > 1, tails shorter than a chunk."""
+    from smilecode_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(batch, cin, *shape, generator=g)
+    gy = torch.randn(batch, cout, *shape, generator=g)
+    w = torch.zeros(cout, cin, 3, 3, 3)
+
+    def ref_grads(xx, gg):
+        wr = w.clone().double().requires_grad_(True)
+        br = torch.zeros(cout, dtype=torch.float64, requires_grad=True)
+        (torch.nn.functional.conv3d(xx.double(), wr, br, padding=1) * gg.double()).sum().backward()
+        return wr.grad.float(), br.grad.float()
+
+    with ops.conv_precision("bf16"):
+        _, dw, db = ops.conv3d_bwd(dev(gy), dev(x), dev(w), need_x=False)
+    dw_r, db_r = ref_grads(x, gy)
+    dw_q, _ = ref_grads(x.bfloat16().float(), gy.bfloat16().float())
+    assert rel(dw.cpu(), dw_q) <= 2e-5, (cin, cout, shape)
+    assert rel(dw.cpu(), dw_r) <= 1e-2
+    assert rel(db.cpu(), db_r) <= 1e-5
+
+
 def test_losses_backward():
     from smilecode_b200.autograd import Grad3dLoss, NCCLoss
     from smilecode_b200.synth import make_pair

@@ -1,6 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_backward.py -x -q 2>&1 | tail -3
-timeout 600 python tools/train_breakdown.py > gpurun_out/r04e_train_breakdown_fp32.txt 2>&1
-head -12 gpurun_out/r04e_train_breakdown_fp32.txt; grep "warp3d_bwd\[" gpurun_out/r04e_train_breakdown_fp32.txt | head
-SMILE_WARP_BWD_PLAIN=1 timeout 600 python tools/train_breakdown.py 2>&1 | grep -E "^step|warp3d_bwd" | head -6
+timeout 900 python -m pytest tests/test_gpu_backward.py tests/test_gpu_parity.py -x -q -k "tensor_cores or bf16 or train" 2>&1 | tail -3
+SMILE_TRAIN_DTYPE=bf16 timeout 600 python tools/train_breakdown.py > gpurun_out/r04f_train_breakdown_bf16.txt 2>&1
+head -12 gpurun_out/r04f_train_breakdown_bf16.txt
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value', d['value'], 'train', d['train']['ms_per_step'], 'bf16', d['train_bf16']['ms_per_step'], d['train_bf16'].get('value'))"

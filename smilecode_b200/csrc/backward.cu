@@ -296,6 +296,42 @@ __global__ void __launch_bounds__(128) attn_bwd_dk_kernel(const float* __restric
   }
 }
 
+// heads == 1, head_dim == 6 (the two large levels): accumulators in registers, 32-bit indices, taps fully unrolled.
+// (The generic kernel above indexes acc[] with a run-time head_dim: local memory; 0.46 ms per call at 160x192x160.)
+__global__ void __launch_bounds__(128) attn_bwd_dk6_kernel(const float* __restrict__ dl, const float* __restrict__ q,
+                                                           float* __restrict__ dk, int D, int H, int W, float scale) {
+  const int HW = H * W, N = D * HW;
+  const int b = blockIdx.y;
+  const float* qb = q + (long long)b * N * 6;
+  const float* dlb = dl + (long long)b * N * 27;
+  float* dkb = dk + (long long)b * N * 6;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
+    const int d = p / HW;
+    const int r = p - d * HW;
+    const int h = r / W, w = r - h * W;
+    float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+      // query voxel n whose tap t is this key voxel: n = m - off(t)
+      const int od = t / 9 - 1, oh = (t / 3) % 3 - 1, ow = t % 3 - 1;
+      const int dd = d - od, hh = h - oh, ww = w - ow;
+      if ((unsigned)dd < (unsigned)D && (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W) {
+        const int n = p - (od * HW + oh * W + ow);
+        const float gv = __ldg(dlb + t * N + n);
+        const float2* qr = reinterpret_cast<const float2*>(qb + (long long)n * 6);
+        const float2 q0 = __ldg(qr), q1 = __ldg(qr + 1), q2 = __ldg(qr + 2);
+        a0.x = fmaf(gv, q0.x, a0.x); a0.y = fmaf(gv, q0.y, a0.y);
+        a1.x = fmaf(gv, q1.x, a1.x); a1.y = fmaf(gv, q1.y, a1.y);
+        a2.x = fmaf(gv, q2.x, a2.x); a2.y = fmaf(gv, q2.y, a2.y);
+      }
+    }
+    float2* o = reinterpret_cast<float2*>(dkb + (long long)p * 6);
+    o[0] = make_float2(a0.x * scale, a0.y * scale);
+    o[1] = make_float2(a1.x * scale, a1.y * scale);
+    o[2] = make_float2(a2.x * scale, a2.y * scale);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // ProjectionLayer backward.  z = W x + b; y = gamma * (z - mean) * rstd + beta.
 // ------------------------------------------------------------------------------------------------
@@ -617,7 +653,10 @@ int launch_modet_attn_bwd(const float* g, const float* q, const float* k, const 
     rc = check_launch("modet_attn_bwd(dq)");
     if (rc) return rc;
   }
-  attn_bwd_dk_kernel<<<grid, 128, 0, st>>>(dl_work, q, dk, D, H, W, heads, hd, scale);
+  if (heads == 1 && hd == 6 && (long long)D * H * W * 27 < (1LL << 31))
+    attn_bwd_dk6_kernel<<<grid, 128, 0, st>>>(dl_work, q, dk, D, H, W, scale);
+  else
+    attn_bwd_dk_kernel<<<grid, 128, 0, st>>>(dl_work, q, dk, D, H, W, heads, hd, scale);
   return check_launch("modet_attn_bwd(dk)");
 }
 

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-SMILE_WGRAD_TC=2 timeout 900 ncu --set full --clock-control none --import-source on -k regex:wgrad_tc -c 1 -o gpurun_out/r04g_wgrad_tc -f python tools/run_wgrad_tc.py > gpurun_out/job19_ncu.log 2>&1
-tail -2 gpurun_out/job19_ncu.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r04_train_launches.csv python tools/train_breakdown.py > gpurun_out/job19.log 2>&1
+tail -2 gpurun_out/job19.log

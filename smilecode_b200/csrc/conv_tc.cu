@@ -212,33 +212,47 @@ conv3d_tc_kernel(const float* __restrict__ in, const float* __restrict__ wprep, 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
     __syncthreads();
 
-    // ---- one thread issues the 54 MMAs of the stage (two per tap)
-    if (tid == 0) {
-      mbar_wait(smem_u32(bars), ph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + (uint32_t)a_plane * 16, b_base = smem_u32(sB);
-      int g = 0;
-      for (int tap = 0; tap < 27; ++tap) {
-        if (tap >= kGroupStart[g + 1]) ++g;
-        const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-        const uint32_t a_off = (uint32_t)((kd * 2 * SEG + (Wp + 1) + (kh - 1) * Wp + (kw - 1)) * 16);
-        const uint32_t b_off = (uint32_t)(tap * 2 * 2 * NT * 16);   // [tap][cb][hi/lo][NT][4]: cb stride = 2*NT*16
-        const uint32_t dcol = tmem + (uint32_t)(g * 2 * NT);
-        // A_hi x [B_hi | B_lo]  (N = 2*NT: hi*hi into columns [0,NT), hi*lo into [NT,2NT)), then A_lo x B_hi into [0,NT)
+    // ---- one thread issues the 54 MMAs of the stage (two per tap).  It is chosen with elect.sync -- the compiler then feeds
+    // UTCHMMA from uniform registers instead of expanding every tcgen05.mma into a per-lane ELECT / R2UR / branch loop -- and a
+    // descriptor is a 32-bit add on its low word (start address; LBO in bits 16-29), the high word (SBO = 128 B, version) is
+    // the constant 0x4008 (see conv_march.cu).
+    if (warp == 0) {
+      uint32_t leader = 0;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+      if (leader) {
+        mbar_wait(smem_u32(bars), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi16 = (smem_u32(sA) >> 4) | ((uint32_t)SEG << 16);           // LBO = one staged plane of SEG positions
+        const uint32_t a_lo16 = a_hi16 + (uint32_t)a_plane;
+        const uint32_t b16 = (smem_u32(sB) >> 4) | ((uint32_t)(2 * NT) << 16);         // LBO = 2 * NT rows x 16 B
+        auto desc64 = [](uint32_t lo) {
+          uint64_t dsc;
+          asm("mov.b64 %0, {%1, %2};" : "=l"(dsc) : "r"(lo), "r"(0x4008u));
+          return dsc;
+        };
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-          const uint64_t da = make_desc((pass == 1 ? a_lo : a_hi) + a_off, (uint32_t)SEG * 16, 128);
-          const uint64_t db = make_desc(b_base + b_off, 2 * NT * 16, 128);
-          const uint32_t accum = (tap > kGroupStart[g] || pass > 0) ? 1u : 0u;
-          asm volatile(
-              "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-              "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-              ::"r"(dcol), "l"(da), "l"(db), "r"(pass == 0 ? idesc_2n : idesc_n), "r"(accum)
-              : "memory");
+        for (int tap = 0; tap < 27; ++tap) {
+          const int g = tap < 7 ? 0 : tap < 14 ? 1 : tap < 21 ? 2 : 3;                 // kGroupStart = {0, 7, 14, 21, 27}
+          const int gstart = g * 7;
+          const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+          const uint32_t a_off = (uint32_t)(kd * 2 * SEG + (Wp + 1) + (kh - 1) * Wp + (kw - 1));
+          const uint32_t b_off = (uint32_t)(tap * 2 * 2 * NT);   // [tap][cb][hi/lo][NT][4]: cb stride = 2*NT*16 B
+          const uint32_t dcol = tmem + (uint32_t)(g * 2 * NT);
+          // A_hi x [B_hi | B_lo]  (N = 2*NT: hi*hi into columns [0,NT), hi*lo into [NT,2NT)), then A_lo x B_hi into [0,NT)
+          const uint64_t db = desc64(b16 + b_off);
+          if (tap == gstart)
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                         ::"r"(dcol), "l"(desc64(a_hi16 + a_off)), "l"(db), "r"(idesc_2n) : "memory");
+          else
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                         ::"r"(dcol), "l"(desc64(a_hi16 + a_off)), "l"(db), "r"(idesc_2n) : "memory");
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                       ::"r"(dcol), "l"(desc64(a_lo16 + a_off)), "l"(db), "r"(idesc_n) : "memory");
         }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bars + 1))
+                     : "memory");
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bars + 1))
-                   : "memory");
+      __syncwarp();
     }
     // ---- drain the accumulator groups into registers (round-to-nearest adds)
     mbar_wait(smem_u32(bars + 1), ph);

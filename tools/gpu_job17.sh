@@ -1,7 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "conv" 2>&1 | tail -3
-for S in 1 2; do
-echo "=== SMILE_CONV_SPLIT=$S"
-SMILE_CONV_SPLIT=$S timeout 600 python tools/conv_compare.py 2>&1 | grep -E "160x192x160|80x96x80|total"
-done
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "conv" 2>&1 | tail -2
+SMILE_CONV_SPLIT=1 timeout 600 python tools/conv_compare.py 2>&1 | grep -E "40x48x40|20x24x20|10x12x10|total"

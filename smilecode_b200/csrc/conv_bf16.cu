@@ -191,26 +191,38 @@ conv3d_bf16_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
     __syncthreads();
 
-    // ---- one thread issues the 27 MMAs of the stage; they run while the other buffer is being staged
-    if (tid == 0) {
-      mbar_wait(smem_u32(bars + buf), use & 1u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_base = smem_u32(sAb), b_base = smem_u32(sB + buf * B_BYTES);
-      for (int tap = 0; tap < 27; ++tap) {
-        const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-        const uint32_t a_off = (uint32_t)((kd * 2 * SEG + (Wp + 1) + (kh - 1) * Wp + (kw - 1)) * 16);
-        const uint32_t b_off = (uint32_t)(tap * 2 * NT * 16);
-        const uint64_t da = make_desc(a_base + a_off, (uint32_t)SEG * 16, 128);
-        const uint64_t db = make_desc(b_base + b_off, NT * 16, 128);
-        const uint32_t accum = (stage > 0 || tap > 0) ? 1u : 0u;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accum)
-            : "memory");
+    // ---- one thread issues the 27 MMAs of the stage; they run while the other buffer is being staged.  The thread is
+    // chosen with elect.sync and a descriptor is a 32-bit add on its low word (see conv_march.cu: with `tid == 0` ptxas
+    // expanded every tcgen05.mma into a per-lane ELECT / R2UR / branch loop).
+    if (warp == 0) {
+      uint32_t leader = 0;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+      if (leader) {
+        mbar_wait(smem_u32(bars + buf), use & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a16 = (smem_u32(sAb) >> 4) | ((uint32_t)SEG << 16);                   // LBO = one plane of SEG positions
+        const uint32_t b16 = (smem_u32(sB + buf * B_BYTES) >> 4) | ((uint32_t)NT << 16);     // LBO = NT rows x 16 B
+        auto desc64 = [](uint32_t lo) {
+          uint64_t dsc;
+          asm("mov.b64 %0, {%1, %2};" : "=l"(dsc) : "r"(lo), "r"(0x4008u));
+          return dsc;
+        };
+#pragma unroll
+        for (int tap = 0; tap < 27; ++tap) {
+          const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+          const uint32_t a_off = (uint32_t)(kd * 2 * SEG + (Wp + 1) + (kh - 1) * Wp + (kw - 1));
+          const uint32_t b_off = (uint32_t)(tap * 2 * NT);
+          const uint32_t accum = (stage > 0 || tap > 0) ? 1u : 0u;
+          asm volatile(
+              "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+              ::"r"(tmem), "l"(desc64(a16 + a_off)), "l"(desc64(b16 + b_off)), "r"(idesc), "r"(accum)
+              : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bars + 2 + buf))
+                     : "memory");
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bars + 2 + buf))
-                   : "memory");
+      __syncwarp();
     }
   }
   // ---- all MMAs done (the last commit tracks every MMA issued before it)

@@ -206,7 +206,7 @@ __global__ void conv_march_prep_split_kernel(const float* __restrict__ w, __half
 // neighbour, so a 16-byte K chunk is TWO taps (kw, kw+1) and a K = 16 MMA covers a whole kernel row (kw = 0, 1 | 2, -):
 // 9 MMAs per M tile and operand set instead of 15.
 template <bool CIN8, bool NORM, int SP, bool CIN4>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, 2)   // 18 warps per SM = 5 on one scheduler: 16384 / (5 x 32) -> 96 registers
 conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, const float* __restrict__ bias,
                   float* __restrict__ out, const double* __restrict__ in_stats, double* __restrict__ out_stats, int Cin,
                   int Cout, int D, int H, int W, int ntr, int ntc, int DS, int act_out, float eps, int CinT, int ci0, int pass) {
@@ -386,6 +386,20 @@ conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, 
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr));
   };
+  // pass 2 adds the partial sums the first launch stored: pull those lines into L1 BEFORE waiting for the MMAs, so that
+  // the four dependent load rounds of the drain hit L1 instead of exposing an L2 round trip each
+  auto prefetch_partial = [&](int dd) {
+#pragma unroll
+    for (int mm = 0; mm < 2; ++mm) {
+      const int h = h0 + 4 * (mbase + mm) + q;
+      if (col_ok && h < H) {
+        const float* ob = out + (long long)b * Cout * N + (long long)dd * HW + h * W + (w0 + lane);
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+          if (n < Cout) asm volatile("prefetch.global.L1 [%0];" ::"l"(ob + (long long)n * N));
+      }
+    }
+  };
   auto drain_plane = [&](int dd, int buf) {
 #pragma unroll
     for (int mm = 0; mm < 2; ++mm) {
@@ -449,6 +463,7 @@ conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, 
       arrive(3 + par);                                               // planes d-1, d, d+1 are in the ring
       if (d > d0) {
         const int pb = par ^ 1;
+        if (pass == 2) prefetch_partial(d - 1);
         mbar_wait(smem_u32(bars + 1 + pb), ph[pb]);                  // MMAs of plane d-1 complete
         ph[pb] ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -460,6 +475,7 @@ conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, 
     }
     {
       const int pb = (d1 - 1 - d0) & 1;
+      if (pass == 2) prefetch_partial(d1 - 1);
       mbar_wait(smem_u32(bars + 1 + pb), ph[pb]);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       drain_plane(d1 - 1, pb);

@@ -116,7 +116,7 @@ def test_projection_golden(ops, name):
                                             # TMA-staged kernel: 32- and 16-wide tiles, partial tiles, odd channel counts
                                             (8, 16, (9, 10, 64)), (16, 16, (5, 12, 80)), (4, 8, (10, 9, 160)),
                                             (3, 5, (11, 7, 20)), (24, 48, (4, 6, 20)), (6, 12, (17, 3, 48)),
-                                            (32, 32, (8, 9, 40)), (1, 4, (3, 20, 96)),
+                                            (32, 32, (8, 9, 40)), (1, 4, (3, 20, 96)), (1, 3, (9, 17, 36)), (1, 2, (19, 8, 16)),
                                             # small-volume channel-lane kernel (W <= 16, Cout >= 16)
                                             (64, 128, (10, 12, 10)), (7, 20, (3, 5, 13)), (16, 70, (2, 9, 4)), (5, 33, (6, 2, 16))])
 def test_conv3d_oracle(ops, cin, cout, shape):

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "fp16_split" 2>&1 | tail -2
-SMILE_CONV_SPLIT=1 timeout 600 python tools/conv_compare.py 2>&1 | grep -E "16->16|8->16|total"
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "conv3d_oracle or end_to_end or encoder" 2>&1 | tail -2
+timeout 300 python tools/run_kernel.py conv1 7 2>&1 | tail -1

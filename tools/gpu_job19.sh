@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r04_train_launches.csv python tools/train_breakdown.py > gpurun_out/job19.log 2>&1
-tail -2 gpurun_out/job19.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "upsample or end_to_end or cwm" 2>&1 | tail -2
+timeout 600 python tools/run_upsample.py

@@ -373,6 +373,7 @@ int smile_conv3d_wgrad_bf16(const float* in, const float* d_out, float* d_w, flo
   REQUIRE_PTR(d_w);
   REQUIRE_VOL(B, D, H, W);
   REQUIRE(Cin > 0 && Cout > 0 && Cin <= 4096 && Cout <= 4096, "%s: Cin=%d Cout=%d out of range", __func__, Cin, Cout);
+  REQUIRE(B <= 65535, "%s: B=%d exceeds grid.z of the full-precision fallback", __func__, B);
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(d_w, 0, (size_t)Cout * Cin * 27 * sizeof(float), st) != cudaSuccess ||
       (d_b != nullptr && cudaMemsetAsync(d_b, 0, (size_t)Cout * sizeof(float), st) != cudaSuccess)) {

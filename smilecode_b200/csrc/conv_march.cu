@@ -605,8 +605,26 @@ int launch_march(const float* in, const float* weight, const float* bias, float*
   // Two CTAs per SM (92-107 KB of shared memory, 128 / 256 TMEM columns each): while one stages / drains, the other's MMAs
   // run.  The depth is split so that the grid is just under two full waves of 2 x 148 CTAs (measured: 288-576 CTAs beat
   // 144 and anything that leaves a partial third wave; each split re-stages two halo planes, which is not what bounds it).
-  static const int want = [] { const char* e = getenv("SMILE_MARCH_CTAS"); return e ? atoi(e) : 4 * kNumSMs; }();
-  int DS = (int)(want / tiles);
+  // The fp16-split mode (twice the MMAs per plane, so the halo planes of a split weigh less against its tail balance) is
+  // best with the FEWEST depth splits that fill whole waves of 2 x 148 CTAs: 8->8 @160x192x160 (144 tiles) 494 -> 488 us with
+  // 2 splits instead of 4, 16->16 @80x96x80 284 -> 272, 8->16 103 -> 92; 160x192x224 (192 tiles) needs 3.
+  static const int knob = [] { const char* e = getenv("SMILE_MARCH_CTAS"); return e ? atoi(e) : 0; }();
+  int DS;
+  if (knob > 0 || SP == 0) {
+    DS = (int)((knob > 0 ? knob : 4 * kNumSMs) / tiles);
+  } else {
+    const long long wave = 2LL * kNumSMs;
+    double best = -1.0;
+    DS = 1;
+    for (int cand = 1; cand <= 8; ++cand) {
+      const long long ctas = tiles * cand;
+      const double eff = (double)ctas / (double)(ceil_div_ll(ctas, wave) * wave);
+      if (eff > best + 0.02) {      // a larger split count has to fill the waves noticeably better
+        best = eff;
+        DS = cand;
+      }
+    }
+  }
   if (DS > D / 4) DS = D / 4;
   if (DS < 1) DS = 1;
   static std::once_flag once[64];

@@ -463,7 +463,7 @@ conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, 
       arrive(3 + par);                                               // planes d-1, d, d+1 are in the ring
       if (d > d0) {
         const int pb = par ^ 1;
-        if (pass == 2) prefetch_partial(d - 1);
+        if (SP != 0 && pass == 2) prefetch_partial(d - 1);
         mbar_wait(smem_u32(bars + 1 + pb), ph[pb]);                  // MMAs of plane d-1 complete
         ph[pb] ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -475,7 +475,7 @@ conv_march_kernel(const float* __restrict__ in, const void* __restrict__ wprep, 
     }
     {
       const int pb = (d1 - 1 - d0) & 1;
-      if (pass == 2) prefetch_partial(d1 - 1);
+      if (SP != 0 && pass == 2) prefetch_partial(d1 - 1);
       mbar_wait(smem_u32(bars + 1 + pb), ph[pb]);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       drain_plane(d1 - 1, pb);

@@ -1,19 +1,24 @@
 // Conv3d 3x3x3 / pad 1 for the WIDE, few-channel levels (Cin <= 16, Cout <= 16: the 160- and 80-wide encoder / CWM layers,
-// 70 % of the convolution time) with bf16 operands on tcgen05 -- the depth-marching counterpart of conv_bf16.cu.
+// 70 % of the convolution time) on tcgen05 -- the depth-marching counterpart of conv_bf16.cu / conv_tc.cu.  Two precisions
+// (template parameter SP, struct Lay): bf16 operands for the bf16 mode (BASELINE.json configs[2..3]) and fp16-split operands
+// (x = hi + 2^-11 lo, three products) with fp32-class accuracy for the default fp32 path.
 //
 // conv_bf16.cu stages three padded planes per 128 outputs; on a 160-wide volume that is 10 staged positions per output
 // and the kernel is 5-10x slower than the fp32 SIMT path (profiles/r03e_conv_compare.txt).  Here a CTA owns a 16-row x
 // 30-column tile of the (H, W) plane and marches it along D:
-//   * every input plane of the tile (18 x 32 positions with halo, position-major, 16 bf16 channels = 2 x 16 bytes per
-//     position) is staged ONCE into a ring of four planes -- 1.2 staged positions per output;
-//   * with Cin <= 16 the whole reduction over input channels is one K = 16 MMA per tap: 27 MMAs per 128-position M tile,
-//     four M tiles (4 rows x 32 padded columns each) per plane; a tap (kd, kh, kw) is ring slot kd and the shifted
-//     start address (kh * 32 + kw) * 16 B of a K-major no-swizzle A descriptor, as in conv_tc.cu / conv_bf16.cu;
-//   * two TMEM accumulator buffers (4 x 16 columns each) and a dedicated MMA-issuing warp: the MMAs of plane d run while
-//     the eight worker warps stage plane d+2 and drain, bias-add and store plane d-1; the hand-overs are mbarriers
-//     (plane staged -> issuer, MMAs done -> workers, buffer drained -> issuer), there is no CTA-wide barrier in the loop;
-//   * InstanceNorm statistics of the raw output are kept in registers for the whole march and reduced once.
-// Contract identical to smile_conv3d_bf16_fwd (NCDHW fp32 in / out, normalise-on-load, fp64 statistics).
+//   * every input plane of the tile (18 x 32 positions with halo, position-major, 8 channels = 16 bytes per position and
+//     channel block) is staged ONCE into a ring of four planes -- 1.2 staged positions per output;
+//   * a tap (kd, kh, kw) is ring slot kd and the shifted start address (kh * 32 + kw) * 16 B of a K-major no-swizzle A
+//     descriptor, as in conv_tc.cu / conv_bf16.cu; four M tiles (4 rows x 32 padded columns each) per plane.  With more than 8
+//     input channels the K = 16 MMA is one tap x 16 channels (27 MMAs per M tile), with 5..8 it is TWO taps x 8 channels (the
+//     descriptor's leading-dimension offset is the distance between the taps: 15 MMAs), with <= 4 a staged position also
+//     carries its right-hand neighbour's channels and one MMA covers a kernel row (9 MMAs);
+//   * two TMEM accumulator buffers and a dedicated MMA-issuing warp (one elect.sync thread, 32-bit descriptor arithmetic on
+//     the uniform datapath): the MMAs of plane d run while the eight worker warps stage plane d+2 and drain, bias-add and
+//     store plane d-1; the hand-overs are mbarriers (plane staged -> issuer, MMAs done -> workers, buffer drained -> issuer),
+//     there is no CTA-wide barrier in the loop;
+//   * InstanceNorm statistics of the raw output: fp32 partials flushed every four planes into per-warp fp64 sums.
+// Contract identical to smile_conv3d_fwd / smile_conv3d_bf16_fwd (NCDHW fp32 in / out, normalise-on-load, fp64 statistics).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 

@@ -11,6 +11,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -67,6 +68,13 @@ constexpr int G_BYTES = CO * 4 * 32 * 4;   // 2048
 constexpr int SLOT = X_STRIDE + G_BYTES;   // 3072
 constexpr int OFF_BAR = NSL * SLOT;
 constexpr int SMEM = OFF_BAR + NSL * 8;
+// two-row variant (a thread owns the voxel pair (h, w), (h + 1, w): 8 rows x 32 columns per CTA)
+constexpr int X2_BYTES = 10 * XPW * 4;      // 1600
+constexpr int X2_STRIDE = 1664;             // 128-byte multiple
+constexpr int G2_BYTES = CO * 8 * 32 * 4;   // 4096
+constexpr int SLOT2 = X2_STRIDE + G2_BYTES; // 5760
+constexpr int OFF_BAR2 = NSL * SLOT2;
+constexpr int SMEM2 = OFF_BAR2 + NSL * 8;
 
 __global__ void __launch_bounds__(128) conv3d_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                const __grid_constant__ CUtensorMap tm_g,
@@ -171,6 +179,123 @@ __global__ void __launch_bounds__(128) conv3d_wgrad_tma_kernel(const __grid_cons
   }
 }
 
+// Two voxels (h, w), (h + 1, w) per thread; otherwise the kernel above.
+__global__ void __launch_bounds__(128) conv3d_wgrad_tma2_kernel(const __grid_constant__ CUtensorMap tm_x,
+                                                               const __grid_constant__ CUtensorMap tm_g,
+                                                               float* __restrict__ dw, float* __restrict__ db, int Cin,
+                                                               int Cout, int D, int dchunk, int tiles_h, int tiles_w) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ float s_part[4][CO * 27 + CO];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + OFF_BAR2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int t = blockIdx.x;
+  const int tw = t % tiles_w;
+  t /= tiles_w;
+  const int th = t % tiles_h;
+  const int dc = t / tiles_h;
+  const int b = blockIdx.z;
+  const int cog = blockIdx.y / Cin, ci = blockIdx.y % Cin;
+  const int co0 = cog * CO;
+  const int h0 = th * 8, w0 = tw * 32;
+  const int d_begin = dc * dchunk, d_end = min(D, d_begin + dchunk);
+  const int p_first = d_begin - 1, p_last = d_end;  // planes staged: input needs d-1 .. d+1
+
+  if (tid == 0) {
+    for (int i = 0; i < NSL; ++i) mbar_init(bar0 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int p) {  // called by thread 0 only
+    const int q = p - p_first;
+    const uint32_t slot = sbase + (q % NSL) * SLOT2, bar = bar0 + 8 * (q % NSL);
+    mbar_expect_tx(bar, X2_BYTES + G2_BYTES);
+    tma_load_5d(slot, &tm_x, bar, w0 - 4, h0 - 1, p, ci, b);
+    tma_load_5d(slot + X2_STRIDE, &tm_g, bar, w0, h0, p, co0, b);
+  };
+  if (tid == 0)
+    for (int p = p_first; p <= p_last && p < p_first + AHEAD; ++p) issue(p);
+  int next_p = p_first + AHEAD;
+
+  float2 acc[CO / 2][27];
+  float bsum[CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) bsum[c] = 0.f;
+#pragma unroll
+  for (int c = 0; c < CO / 2; ++c)
+#pragma unroll
+    for (int k = 0; k < 27; ++k) acc[c][k] = make_float2(0.f, 0.f);
+
+  // planes d_begin-1 and d_begin must have landed before the first step
+  mbar_wait(bar0, 0);
+  if (p_first + 1 <= p_last) mbar_wait(bar0 + 8, 0);
+  for (int d = d_begin; d < d_end; ++d) {
+    const int q1 = d + 1 - p_first;  // ring index of plane d+1
+    mbar_wait(bar0 + 8 * (q1 % NSL), (q1 / NSL) & 1);
+    const int qm = q1 - 2, q0 = q1 - 1;
+    // the pair's output gradients: rows 2 * warp (A) and 2 * warp + 1 (B) of the 8-row tile, [co][row][col]
+    const float* gs = reinterpret_cast<const float*>(smem + (q0 % NSL) * SLOT2 + X2_STRIDE) + (2 * warp) * 32 + lane;
+    float gA[CO], gB[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+      gA[c] = gs[c * 256];
+      gB[c] = gs[c * 256 + 32];
+    }
+#pragma unroll
+    for (int c = 0; c < CO; ++c) bsum[c] += gA[c] + gB[c];
+    const float2 gA01 = make_float2(gA[0], gA[1]), gA23 = make_float2(gA[2], gA[3]);
+    const float2 gB01 = make_float2(gB[0], gB[1]), gB23 = make_float2(gB[2], gB[3]);
+    // 36 input values (4 rows x 3 columns per plane) feed 108 packed FMAs: the one-voxel kernel reads 27 + 4 values per 54
+    // and is bound by the issue of its shared-memory loads
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+      const float* pl = reinterpret_cast<const float*>(smem + ((qm + kd) % NSL) * SLOT2) + (2 * warp) * XPW + lane + 3;
+      float xr[4][3];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) xr[rr][kw] = pl[rr * XPW + kw];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const float xa = xr[j / 3][j % 3], xb = xr[j / 3 + 1][j % 3];
+        acc[0][kd * 9 + j] = fma2(make_float2(xa, xa), gA01, acc[0][kd * 9 + j]);
+        acc[1][kd * 9 + j] = fma2(make_float2(xa, xa), gA23, acc[1][kd * 9 + j]);
+        acc[0][kd * 9 + j] = fma2(make_float2(xb, xb), gB01, acc[0][kd * 9 + j]);
+        acc[1][kd * 9 + j] = fma2(make_float2(xb, xb), gB23, acc[1][kd * 9 + j]);
+      }
+    }
+    __syncthreads();  // every warp is done with plane d-1
+    // one new plane per step keeps AHEAD planes in flight; its slot held plane (next_p - NSL) <= d - 1: free
+    if (tid == 0 && next_p <= p_last) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(next_p);
+    }
+    ++next_p;
+  }
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      const float v = warp_sum((c & 1) ? acc[c / 2][k].y : acc[c / 2][k].x);
+      if (lane == 0) s_part[warp][c * 27 + k] = v;
+    }
+    const float v = warp_sum(bsum[c]);
+    if (lane == 0) s_part[warp][CO * 27 + c] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < CO * 27 + CO; i += 128) {
+    const float v = s_part[0][i] + s_part[1][i] + s_part[2][i] + s_part[3][i];
+    if (i < CO * 27) {
+      const int c = i / 27, k = i % 27;
+      if (co0 + c < Cout) atomicAdd(dw + ((long long)(co0 + c) * Cin + ci) * 27 + k, v);
+    } else if (ci == 0 && db != nullptr) {
+      const int c = i - CO * 27;
+      if (co0 + c < Cout) atomicAdd(db + co0 + c, v);
+    }
+  }
+}
+
 PFN_cuTensorMapEncodeTiled get_encode() {
   static PFN_cuTensorMapEncodeTiled fn = nullptr;
   static std::once_flag once;
@@ -209,23 +334,28 @@ int launch_conv3d_wgrad_tma(const float* x, const float* dy, float* dw, float* d
   const long long groups = (long long)ceil_div(Cout, CO) * Cin;
   if (groups > 65535) return SMILE_OK;
   *handled = true;
+  static const bool one_row = getenv("SMILE_WGRAD_ONE_ROW") != nullptr;   // A/B knob
+  const bool two = H >= 8 && !one_row;
+  const int TROWS = two ? 8 : 4;
   CUtensorMap tx, tg;
-  const cuuint32_t bx[5] = {XPW, 6, 1, 1, 1}, bg[5] = {32, 4, 1, CO, 1};
+  const cuuint32_t bx[5] = {XPW, (cuuint32_t)(TROWS + 2), 1, 1, 1}, bg[5] = {32, (cuuint32_t)TROWS, 1, CO, 1};
   if (!encode5(&tx, x, W, H, D, Cin, B, bx) || !encode5(&tg, dy, W, H, D, Cout, B, bg)) return SMILE_ERR_CUDA;
-  const int tiles_h = ceil_div(H, 4), tiles_w = ceil_div(W, 32);
+  const int tiles_h = ceil_div(H, TROWS), tiles_w = ceil_div(W, 32);
   const long long per_plane = (long long)tiles_h * tiles_w * groups * B;
   int chunks = (int)ceil_div_ll(4LL * kNumSMs * 4, per_plane);
   if (chunks < 1) chunks = 1;
   int dchunk = ceil_div(D, chunks);
   if (dchunk < 8) dchunk = D < 8 ? D : 8;
   chunks = ceil_div(D, dchunk);
-  cudaError_t e = cudaFuncSetAttribute(conv3d_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  const int smem = two ? SMEM2 : SMEM;
+  auto kern = two ? conv3d_wgrad_tma2_kernel : conv3d_wgrad_tma_kernel;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) {
-    set_error("conv3d_wgrad(TMA): cannot reserve %d B of shared memory: %s", SMEM, cudaGetErrorString(e));
+    set_error("conv3d_wgrad(TMA): cannot reserve %d B of shared memory: %s", smem, cudaGetErrorString(e));
     return SMILE_ERR_CUDA;
   }
   dim3 grid(tiles_h * tiles_w * chunks, (unsigned)groups, B);
-  conv3d_wgrad_tma_kernel<<<grid, 128, SMEM, st>>>(tx, tg, dw, db, Cin, Cout, D, dchunk, tiles_h, tiles_w);
+  kern<<<grid, 128, smem, st>>>(tx, tg, dw, db, Cin, Cout, D, dchunk, tiles_h, tiles_w);
   return check_launch("conv3d_wgrad(TMA)");
 }
 
